@@ -1,0 +1,186 @@
+"""Pins the numpy oracle against the UNMODIFIED reference, imported live.
+
+Runs only where /root/reference exists (authoring container); on the GPU box
+the committed fixtures under tests/golden/ (made by make_golden.py from the
+same reference) take over -- see test_oracle_golden.py.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import frcnn_oracle as O
+from oracle import ref_loader
+from faster_rcnn_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+def _ref_image(ref, name, w, h, gts):
+    S = ref.shapes
+    boxes = [S.GroundTruthBox(c, False, S.Box(x1, y1, x2, y2)) for c, x1, y1, x2, y2 in gts]
+    return S.Image(S.Metadata(name, w, h, boxes, '/nonexistent.jpg'))
+
+
+def test_anchor_tables(ref):
+    for scales in ([128, 256, 512], [16, 32, 64, 128, 256, 512]):
+        assert np.array_equal(O.anchor_table(scales), ref.util.get_anchors(scales))
+    assert np.array_equal(O.anchor_table(), ref.shared_constants.DEFAULT_ANCHORS)
+
+
+@pytest.mark.parametrize("rows,cols,scales,seed", [(38, 63, [128, 256, 512], 1), (38, 94, None, 2), (5, 7, [128, 256, 512], 3)])
+def test_proposals_and_topk(ref, rows, cols, scales, seed):
+    dims = O.anchor_table(scales) if scales else O.anchor_table()
+    cls, regr = synth.rpn_outputs(rows, cols, len(dims), seed)
+    with ref_loader.quiet():
+        want = ref.det_util._get_rois(regr.copy(), dims, 16)
+        v = ref.det_util._get_valid_box_idxs(want)
+    got = O.proposals_from_rpn(regr.copy(), dims, 16)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    assert np.array_equal(O.valid_box_indices(got), v)
+    probs = cls.reshape(-1)
+    order = probs[v].argsort()[::-1][:8000]                       # det_util.py:151-153 (tie-free input)
+    b, p, idx = O.topk_proposals(got, probs, 8000)
+    assert np.array_equal(b, want[v][order].astype('int16')) and np.array_equal(p, probs[v][order])
+    assert np.array_equal(idx, v[order])
+
+
+@pytest.mark.parametrize("k,max_boxes,clustered", [(8000, 300, False), (8000, 300, True), (3000, 2000, True)])
+def test_nms_int16(ref, k, max_boxes, clustered):
+    dims = O.anchor_table([128, 256, 512])
+    cls, regr = synth.rpn_outputs(38, 63, 9, 11, clustered=clustered)
+    b, p, _ = O.topk_proposals(O.proposals_from_rpn(regr, dims, 16), cls.reshape(-1), k)
+    with ref_loader.quiet():
+        wb, wp = ref.det_util.nms(b, p, overlap_thresh=0.7, max_boxes=max_boxes)
+    pick = O.greedy_nms(b, p, 0.7, max_boxes)
+    assert np.array_equal(b[pick], wb) and np.array_equal(p[pick], wp)
+    for stable in (True, False):                                   # tie-free: both orders agree
+        gb, gp = O.nms(b, p, 0.7, max_boxes, stable=stable)
+        assert np.array_equal(gb, wb) and np.array_equal(gp, wp)
+
+
+def test_nms_float64_and_empty(ref):
+    rng = np.random.default_rng(5)
+    xy = rng.uniform(0, 500, (400, 2))
+    wh = rng.uniform(5, 200, (400, 2))
+    boxes = np.concatenate([xy, xy + wh], axis=1)
+    probs = rng.permutation(400).astype(np.float32) / 400
+    with ref_loader.quiet():
+        wb, wp = ref.det_util.nms(boxes, probs, overlap_thresh=0.5, max_boxes=2000)
+        assert ref.det_util.nms(boxes[:0], probs[:0]) == []
+    gb, gp = O.nms(boxes, probs, 0.5, 2000)
+    assert np.array_equal(gb, wb) and np.array_equal(gp, wp)
+    assert O.nms(boxes[:0], probs[:0]) == []
+
+
+def test_iou_and_regression_params(ref):
+    rng = np.random.default_rng(9)
+    anc = O.pixel_anchors(38, 63, O.anchor_table([128, 256, 512]), 16)
+    with ref_loader.quiet():
+        assert np.array_equal(anc, ref.rpn_util._get_all_anchor_coords(38, 63, O.anchor_table([128, 256, 512]), 16))
+    gt = np.array([[g[1], g[2], g[3], g[4]] for g in synth.gt_boxes(50, 1000, 600, 4)], dtype=np.float32)
+    with ref_loader.quiet():
+        want = ref.util.cross_ious(anc, gt)
+    got = O.iou_matrix(anc, gt)
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    rois = synth.random_rois(300, 38, 63, 2)
+    with ref_loader.quiet():
+        assert np.array_equal(O.iou_matrix(rois, gt / 16), ref.util.cross_ious(rois, gt / 16))
+    for _ in range(20):
+        a = np.array([10, 20, 138, 148]) + rng.integers(0, 5, 4)
+        assert O.regression_params(a, gt[3]) == ref.util.get_reg_params(a, gt[3])
+
+
+@pytest.mark.parametrize("n_gt,seed", [(50, 1), (3, 2), (1, 3)])
+def test_rpn_labels(ref, n_gt, seed):
+    dims = O.anchor_table([128, 256, 512])
+    gts = synth.gt_boxes(n_gt, 1000, 600, seed)
+    img = _ref_image(ref, 'synth%d' % seed, 1000, 600, gts)
+    mgr = ref.rpn_util.RpnTrainingManager(O.conv_dims_resnet, 16, preprocess_func=None, anchor_dims=dims)
+    with ref_loader.quiet():
+        mgr._process(img)
+    want = mgr._cache[img.cache_key]
+    gt = np.array([g[1:] for g in gts], dtype=np.float32)
+    rows, cols = O.conv_dims_resnet(600, 1000)
+    cu, ip, bb = O.label_anchors(1000, 600, gt, rows, cols, dims, 16)
+    assert np.array_equal(cu, want['can_use']) and np.array_equal(ip, want['is_pos'])
+    assert np.array_equal(bb, want['bbreg_targets'])
+    random.seed(1)
+    with ref_loader.quiet():
+        y_cls, y_reg = mgr.rpn_y_true(img)
+    random.seed(1)
+    cu2 = O.sample_rpn(ip, cu.copy())
+    g_cls, g_reg = O.pack_rpn_targets(cu2, ip, bb, rows, cols, len(dims))
+    assert g_cls.dtype == y_cls.dtype and np.array_equal(g_cls, y_cls)
+    assert g_reg.dtype == y_reg.dtype and np.array_equal(g_reg, y_reg)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_det_labels_and_sampling(ref, seed):
+    gts = synth.gt_boxes(50, 1000, 600, seed)
+    img = _ref_image(ref, 'synth%d' % seed, 1000, 600, gts)
+    rois = synth.random_rois(2000, 38, 63, seed)
+    mapping = synth.VOC_CLASS_MAPPING
+    with ref_loader.quiet():
+        w_rois, w_cls, w_tr = ref.det_util._rois_to_truth(rois, img, mapping, stride=16)
+    gt64 = np.array([[v * (1 / 16) for v in g[1:]] for g in gts], dtype=np.float64)
+    gidx = np.array([mapping[g[0]] for g in gts])
+    g_rois, g_cls, g_tr = O.label_rois(rois, gt64, gidx, len(mapping))
+    assert np.array_equal(g_rois, w_rois) and g_cls.dtype == w_cls.dtype and np.array_equal(g_cls, w_cls)
+    assert g_tr.dtype == w_tr.dtype and np.array_equal(g_tr, w_tr)
+    found = w_cls[:, -1] == 0
+    for flags in (found, np.zeros_like(found), np.ones_like(found), found & (np.arange(len(found)) < 40)):
+        np.random.seed(1337)
+        with ref_loader.quiet():
+            want = ref.det_util._get_det_samples(flags, 64)
+        np.random.seed(1337)
+        assert O.sample_det(flags, 64) == want
+
+
+def test_det_postprocess(ref):
+    """voc_dets.py cannot be imported (Keras), so its loop (voc_dets.py:51-86) is
+    replayed here around the reference's own nms/transform."""
+    mapping = synth.VOC_CLASS_MAPPING
+    rev = {v: k for k, v in mapping.items()}
+    rois = synth.random_rois(320, 37, 62, 3)
+    out_cls, out_reg = synth.detector_outputs(320, 21, 3)
+    ratio, stride = 1.6, 16
+    bb, pp = {}, {}
+    for r in range(320):
+        c = np.argmax(out_cls[r])
+        if c == mapping['bg']:
+            continue
+        x1, y1, x2, y2 = rois[r]
+        t = out_reg[r, c * 4:(c + 1) * 4] / ref.shared_constants.BBREG_MULTIPLIERS
+        px = ref.util.transform([x1, y1, x2, y2], t)
+        bb.setdefault(rev[c], []).append([stride * v for v in px])
+        pp.setdefault(rev[c], []).append(out_cls[r, c])
+    want = []
+    for name in bb:
+        with ref_loader.quiet():
+            nb, npb = ref.det_util.nms(np.array(bb[name]), np.array(pp[name]), overlap_thresh=0.5, max_boxes=2000)
+        for i in range(nb.shape[0]):
+            want.append((mapping[name], [int(round(v / ratio)) for v in nb[i]], npb[i]))
+    got = O.det_postprocess(rois, out_cls, out_reg, mapping['bg'], stride, ratio)
+    assert len(got) == len(want) > 50
+    for (gc, gb, gp), (wc, wb, wp) in zip(got, want):
+        assert gc == wc and list(gb) == wb and gp == wp
+
+
+def test_known_answer_000005(ref):
+    """labelling known-answer on the one shipped VOC image."""
+    img = ref.voc.extract_img_data('/root/reference/test_data/VOC_test', '000005').resize_within_bounds(600, 1000)[0]
+    assert (img.width, img.height) == (800, 600)
+    dims = O.anchor_table([128, 256, 512])
+    gt = ref.util.get_bbox_coords(img.gt_boxes)
+    rows, cols = O.conv_dims_resnet(img.height, img.width)
+    cu, ip, bb = O.label_anchors(img.width, img.height, gt, rows, cols, dims, 16)
+    assert (rows, cols) == (38, 50)
+    assert np.where(ip)[0].tolist() == [7454, 10586, 11036, 11486, 11963, 12413, 12863, 13079, 13529, 13680, 13979]
+    assert int(cu.sum()) == 5287
+    assert abs(float(np.abs(bb).sum()) - 33.408202) < 1e-4
