@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native proposal + NMS + RoI-layer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload C1: ResNet-50 at 600x1000 -> 38x63 feature map, 9 anchors (scales 128/256/512),
+21,546 anchors/image; top-k 8000, NMS 0.7 -> 300 RoIs, padded to 320 = 5x64 rows like the reference, RoI layer
+(crop + bilinear resize to 7x7) on 1024-channel float32 features.  One "step" = this path over one batch of
+`--images-per-gpu` synthetic images per GPU (weak scaling: images are independent, no collective on the path; the
+only exchange is one NCCL all-gather of the final RoIs + counts per step).
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same through the
+public API (`ProposalRoiPipeline.__call__`) with pinned HOST inputs, H2D/D2H inside the timed region;
+`roofline` = RoI-forward kernel (the HBM-bound, dominant kernel) vs the measured copy peak;
+`cpu_baseline` / `--impl reference` = the reference's CPU algorithm (oracle port, pinned bit-exact against the
+reference) on the host cores.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ROWS, COLS, CHANNELS = 38, 63, 1024
+SCALES = [128, 256, 512]
+STRIDE, TOPK, NMS_THRESH, MAX_BOXES, NUM_ROIS, POOL = 16, 8000, 0.7, 300, 64, 7
+PADDED = -(-MAX_BOXES // NUM_ROIS) * NUM_ROIS          # 320
+METRIC = "img/s proposal+NMS+RoIpool @600x1000"
+UNIT = "img/s"
+WORKLOAD = ("C1: ResNet-50 600x1000 -> 38x63x9 anchors (21546/img), top-k 8000, NMS 0.7->300, pad to 320 RoIs, "
+            "RoI crop+bilinear 7x7 on 1024-ch f32 features")
+
+
+def anchor_dims():
+    from faster_rcnn_b200.util import get_anchors
+    return get_anchors(SCALES)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port) on the host cores, image-parallel
+# ------------------------------------------------------------------------------------------------
+_cpu_inputs = None
+
+
+def _cpu_init():
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)          # one image per worker process; no nested BLAS/OpenMP threads
+    except Exception:
+        pass
+
+
+def _cpu_image(i):
+    """one image through the reference's CPU path: decode -> filter -> top-k -> NMS -> pad -> RoI layer."""
+    from oracle import frcnn_oracle as O
+    from oracle import roi_oracle as R
+    cls, regr, feat = _cpu_inputs[i % len(_cpu_inputs)]
+    dims = O.anchor_table(SCALES)
+    boxes = O.proposals_from_rpn(regr.copy(), dims, STRIDE)
+    b, p, _ = O.topk_proposals(boxes, cls.reshape(-1), TOPK)
+    rois, _ = O.nms(b, p, NMS_THRESH, MAX_BOXES)
+    n = len(rois)
+    rows = -(-n // NUM_ROIS) * NUM_ROIS
+    if rows > n:
+        rois = np.concatenate([rois, np.tile(rois[rows - NUM_ROIS], (rows - n, 1))])
+    out = R.roi_resize_fwd(feat[0], rois, POOL)
+    return float(out[0, 0, 0, 0])
+
+
+class CpuArm:
+    def __init__(self, cores=None, n_pre=8):
+        global _cpu_inputs
+        from faster_rcnn_b200 import synth
+        self.cores = cores or len(os.sched_getaffinity(0))
+        _cpu_inputs = []                                     # built before the fork: shared copy-on-write
+        for i in range(n_pre):
+            cls, regr = synth.rpn_outputs(ROWS, COLS, 9, 1000 + i)
+            _cpu_inputs.append((cls, regr, synth.feature_map(ROWS, COLS, CHANNELS, 2000 + i)))
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init)
+        self.pool.map(_cpu_image, range(self.cores))          # warm every worker
+
+    def run(self, n_images):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_image, range(n_images), chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host cores."""
+    if rank != 0:
+        return
+    arm = CpuArm()
+    batch = args.images_per_gpu
+    for _ in range(args.warmup):
+        arm.run(batch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        arm.run(batch)
+    dt = time.perf_counter() - t0
+    arm.close()
+    value = args.steps * batch / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_step": batch, "note": "CPU arm: one step = one batch on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                         "sample": "%d steps x %d images, image-parallel fork pool, %s" % (args.steps, batch, cpu_model())},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v for v in vis.split(",") if v != ""]
+        if local_rank < len(ids) and ids[local_rank].isdigit():
+            return int(ids[local_rank])
+    return local_rank
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roi_traffic_bytes(batch):
+    """dram bytes per RoI-forward launch from the committed ncu capture (profiles/roi_fwd_traffic.json), if any."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "roi_fwd_traffic.json")))
+        if int(t["images_per_launch"]) == batch:
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from faster_rcnn_b200 import parallel, synth
+    from faster_rcnn_b200.pipeline import ProposalRoiPipeline
+    from faster_rcnn_b200.runtime import get_context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback. "
+                         "Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    parallel.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank)
+    ctx = get_context(local_rank)
+    batch = args.images_per_gpu
+    dims = anchor_dims()
+    pipe = ProposalRoiPipeline(dims, STRIDE, TOPK, NMS_THRESH, MAX_BOXES, NUM_ROIS, POOL, "resize", device=local_rank)
+
+    # synthetic inputs (seeded per global image index), resident in HBM, plus pinned host copies for e2e
+    first = rank * batch
+    pairs = [synth.rpn_outputs(ROWS, COLS, len(dims), 1000 + first + i) for i in range(batch)]
+    cls_h = torch.from_numpy(np.concatenate([p[0] for p in pairs])).pin_memory()
+    regr_h = torch.from_numpy(np.concatenate([p[1] for p in pairs])).pin_memory()
+    gen = torch.Generator(device=dev).manual_seed(2000 + rank)
+    feat = torch.randn((batch, ROWS, COLS, CHANNELS), generator=gen, device=dev, dtype=torch.float32)
+    feat_h = torch.empty(feat.shape, dtype=torch.float32).pin_memory()
+    feat_h.copy_(feat)
+    cls, regr = cls_h.to(dev), regr_h.to(dev)
+    ctx.reserve(256 << 20)
+
+    gathered = {}
+
+    def step(events=None):
+        rois, scores, count = pipe_ops.proposals(regr, cls, dims, STRIDE, TOPK, NMS_THRESH, MAX_BOXES)
+        padded, _ = pipe_ops.pad_rois(rois, count, NUM_ROIS)
+        if events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        pooled = pipe_ops.roi_forward(feat, padded, POOL, "resize")
+        if events is not None:
+            e1.record()
+            events.append((e0, e1))
+        if world > 1:      # the path's only exchange: final RoIs + counts, one all-gather each per step
+            if "rois" not in gathered:
+                gathered["rois"] = torch.empty((world * batch, MAX_BOXES, 4), dtype=torch.int16, device=dev)
+                gathered["count"] = torch.empty((world * batch,), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gathered["rois"], rois)
+            dist.all_gather_into_tensor(gathered["count"], count)
+        return rois, count, pooled
+
+    from faster_rcnn_b200 import ops as pipe_ops
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        out = step()
+    fence()
+    count0 = out[1].cpu().numpy()
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = ctx.launches
+    events = []
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    start.record()
+    for _ in range(args.steps):
+        out = step(events)
+    stop.record()
+    fence()
+    launches = ctx.launches - launches0
+    ms = start.elapsed_time(stop)
+    roi_ms = float(np.mean([a.elapsed_time(b) for a, b in events]))
+    del out
+
+    # ---- end to end through the public API: pinned host inputs, H2D + compute + D2H every step -----------------
+    for _ in range(max(1, min(args.warmup, 3))):
+        res = pipe(cls_h, regr_h, feat_h)
+    fence()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def exchange(rois, scores, count):
+        if world > 1:
+            dist.all_gather_into_tensor(gathered["rois"], rois)
+            dist.all_gather_into_tensor(gathered["count"], count)
+
+    e_start.record()
+    for _ in range(args.steps):
+        res = pipe(cls_h, regr_h, feat_h, on_device=exchange)
+    e_stop.record()
+    fence()
+    e2e_ms = e_start.elapsed_time(e_stop)
+    assert np.array_equal(res[2], count0), "e2e path and device path disagree"
+    del res
+    clocks = sampler.stop() if sampler else None
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, roi_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, roi_ms = (float(v) for v in t.cpu())
+
+    if rank == 0:
+        total_images = world * batch * args.steps
+        value = total_images / (ms / 1e3)
+        e2e_value = total_images / (e2e_ms / 1e3)
+        peak, peak_src = measured_peak()
+        algo_bytes = batch * (4 * ROWS * COLS * CHANNELS + 8 * PADDED + 4 * PADDED * POOL * POOL * CHANNELS)
+        achieved = algo_bytes / (roi_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu_per_step": batch, "global_images_per_step": world * batch,
+                       "parallelism": "image-sharded x%d, no hot-path collective, all-gather of final RoIs" % world,
+                       "l2": "inputs larger than L2 (%.0f MB of features + %.0f MB of pooled output per step vs 126 MB L2)"
+                             % (batch * ROWS * COLS * CHANNELS * 4 / 1e6, batch * PADDED * POOL * POOL * CHANNELS * 4 / 1e6),
+                       "rois_per_image": int(count0[0])},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": pipe.h2d_bytes(cls_h, regr_h, feat_h), "d2h_bytes_per_step": pipe.d2h_bytes(batch),
+                    "note": "ProposalRoiPipeline.__call__ on pinned host arrays; RoIs/scores/counts return to the host, "
+                            "pooled features stay on the device for the detector head as in the reference's TF graph"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "roi_fwd_kernel<RESIZE>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": roi_traffic_bytes(batch),
+                         "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": roi_ms, "peak_source": peak_src,
+                         "kernel_share_of_step": roi_ms / (ms / args.steps)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            # separate process: never fork a process that holds a CUDA context
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "0", "--images-per-gpu", str(args.cpu_images)], capture_output=True, text=True)
+            try:
+                ref = json.loads(res.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = dict(ref["cpu_baseline"], sample="%d images of the same workload, image-parallel "
+                                            "fork pool of the numpy oracle (reference algorithm; RoI layer = numpy "
+                                            "restatement of TF-1.3 bilinear), %s" % (args.cpu_images, cpu_model()))
+            except Exception as exc:      # the GPU line must still be printed
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                        "sample": "failed: %r %s" % (exc, res.stderr[-300:])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--images-per-gpu", type=int, default=64)
+    ap.add_argument("--cpu-images", type=int, default=128, help="bounded sample for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+            raise SystemExit(subprocess.call(cmd))
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

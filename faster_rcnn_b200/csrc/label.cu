@@ -1,0 +1,422 @@
+// K-c: training-target assignment.
+//
+//  label_anchors_kernel   anchor x GT IoU (float32, reference op order, no FMA), per-anchor
+//                         max/argmax in registers, per-GT max/argmax with redux.sync warp
+//                         reductions + one packed 64-bit atomicMax per (warp, GT); writes the
+//                         threshold-rule labels and regression targets directly.
+//  label_gt_fixup_kernel  "best anchor of every GT is positive" rule (rpn_util.py:76-82).
+//  count_kernel           #pos&can_use / #neg&can_use per image (needed by host-side sampling).
+//  apply_sampling_kernel  host-drawn switch-offs by rank (rpn_util.py:324-350).
+//  pack_rpn_kernel        Keras y_true layouts (rpn_util.py:125-140).
+//  label_rois_kernel      RoI x GT labelling, compaction, one-hot class / bbreg targets
+//                         (det_util.py:310-366).
+//
+// IoU (util.py:146-177): area1 = (x2-x1)*(y2-y1); inter = max(0,min(x2)-max(x1)) *
+// max(0,min(y2)-max(y1)); iou = inter / ((area1 + area2) - inter); all float32, IEEE division.
+// np.argmax = FIRST maximum on both axes.
+#include "common.cuh"
+
+namespace frcnn {
+
+constexpr int LBL_THREADS = 256;
+
+struct __align__(8) BoxI16 { short x1, y1, x2, y2; };
+
+__device__ __forceinline__ float iou_f32(float ax1, float ay1, float ax2, float ay2, float a_area,
+                                         float gx1, float gy1, float gx2, float gy2, float g_area) {
+  const float w = np_max(0.0f, __fsub_rn(np_min(ax2, gx2), np_max(ax1, gx1)));
+  const float h = np_max(0.0f, __fsub_rn(np_min(ay2, gy2), np_max(ay1, gy1)));
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(a_area, g_area), inter);
+  return __fdiv_rn(inter, uni);
+}
+
+__device__ __forceinline__ void pixel_anchor(int i, const AnchorTable& tab, int cols, int stride,
+                                             int& x1, int& y1, int& x2, int& y2) {
+  const int a = i % tab.n, loc = i / tab.n;
+  const int cx = loc % cols, cy = loc / cols;
+  // int(stride * (c + 0.5)) for non-negative values: exact in double (rpn_util.py:184-189)
+  const int px = (int)((double)stride * ((double)cx + 0.5));
+  const int py = (int)((double)stride * ((double)cy + 0.5));
+  x1 = px - (tab.w[a] >> 1);
+  y1 = py - (tab.h[a] >> 1);
+  x2 = x1 + tab.w[a];
+  y2 = y1 + tab.h[a];
+}
+
+// RPN regression target (util.py:180-206 + rpn_util.py:93): anchor corners are exact ints,
+// GT corners float32; GT centre/size are formed in float32 then everything is float64;
+// the x[10,10,5,5] happens in float64 before the store to float32.
+__device__ __forceinline__ float4 rpn_bbreg(int ax1, int ay1, int ax2, int ay2, float gx1, float gy1,
+                                            float gx2, float gy2) {
+  const double gcx = (double)__fadd_rn(gx2, gx1) / 2.0, gcy = (double)__fadd_rn(gy2, gy1) / 2.0;
+  const double gw = (double)__fsub_rn(gx2, gx1), gh = (double)__fsub_rn(gy2, gy1);
+  const double acx = (double)(ax2 + ax1) / 2.0, acy = (double)(ay2 + ay1) / 2.0;
+  const double aw = (double)(ax2 - ax1), ah = (double)(ay2 - ay1);
+  const double tx = __ddiv_rn(__dsub_rn(gcx, acx), aw), ty = __ddiv_rn(__dsub_rn(gcy, acy), ah);
+  const double tw = log(__ddiv_rn(gw, aw)), th = log(__ddiv_rn(gh, ah));
+  return make_float4((float)__dmul_rn(10.0, tx), (float)__dmul_rn(10.0, ty),
+                     (float)__dmul_rn(5.0, tw), (float)__dmul_rn(5.0, th));
+}
+
+// grid (ceil(N/256), batch).  best_gt [batch, g_max] u64 = (iou_bits << 32) | ~anchor_index,
+// zero-initialised by the caller (IoU >= 0 so float bits order like unsigned ints).
+__global__ void __launch_bounds__(LBL_THREADS)
+label_anchors_kernel(const float* __restrict__ gt_all, const int* __restrict__ n_gt_all,
+                     const int* __restrict__ img_wh, int g_max, AnchorTable tab, int rows, int cols,
+                     int stride, int n, unsigned char* __restrict__ can_use,
+                     unsigned char* __restrict__ is_pos, float4* __restrict__ bbreg,
+                     unsigned long long* __restrict__ best_gt) {
+  __shared__ float4 s_gt[FRCNN_MAX_GT];
+  __shared__ float s_garea[FRCNN_MAX_GT];
+  const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int G = min(n_gt_all[img], g_max);
+  const float* gt = gt_all + (size_t)img * g_max * 4;
+  for (int g = tid; g < G; g += LBL_THREADS) {
+    const float4 b = make_float4(gt[4 * g], gt[4 * g + 1], gt[4 * g + 2], gt[4 * g + 3]);
+    s_gt[g] = b;
+    s_garea[g] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  }
+  __syncthreads();
+
+  const int i = blockIdx.x * LBL_THREADS + tid;
+  const bool live = i < n;
+  int x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+  if (live) pixel_anchor(i, tab, cols, stride, x1, y1, x2, y2);
+  const float fx1 = (float)x1, fy1 = (float)y1, fx2 = (float)x2, fy2 = (float)y2;
+  const float a_area = __fmul_rn(__fsub_rn(fx2, fx1), __fsub_rn(fy2, fy1));
+
+  float best = 0.0f;      // np.amax over a row of the (N,G) matrix; G == 0 cannot happen (guarded on the host)
+  int best_g = 0;
+  bool first = true;
+  for (int g = 0; g < G; ++g) {
+    const float4 b = s_gt[g];
+    float v = live ? iou_f32(fx1, fy1, fx2, fy2, a_area, b.x, b.y, b.z, b.w, s_garea[g]) : 0.0f;
+    if (first || v > best) { best = v; best_g = g; first = false; }   // strict '>' keeps the first maximum
+    // per-GT maximum over anchors, lowest anchor index on ties
+    const unsigned bits = live ? __float_as_uint(v) : 0u;
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+    if (wmax != 0u) {
+      const unsigned who = __ballot_sync(0xffffffffu, live && bits == wmax);
+      if (lane == (__ffs(who) - 1)) {
+        const unsigned long long key = ((unsigned long long)wmax << 32) | (unsigned)(~(unsigned)i);
+        atomicMax(best_gt + (size_t)img * g_max + g, key);
+      }
+    }
+  }
+  if (!live) return;
+
+  const int W = img_wh[2 * img], H = img_wh[2 * img + 1];
+  const bool oob = (x1 < 0) || (y1 < 0) || (x2 >= W) || (y2 >= H);
+  const bool pos = best > 0.7f;                 // rpn_util.py:75 compared in float32
+  const bool neg = !pos && best < 0.3f;         // rpn_util.py:95
+  const size_t o = (size_t)img * n + i;
+  is_pos[o] = pos;
+  can_use[o] = (pos || neg) && !oob;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pos) {
+    const float4 b = s_gt[best_g];
+    t = rpn_bbreg(x1, y1, x2, y2, b.x, b.y, b.z, b.w);
+  }
+  bbreg[o] = t;
+}
+
+// one thread per (GT, image): the arg-max anchor of every GT with max IoU > 0 becomes positive.
+__global__ void label_gt_fixup_kernel(const float* __restrict__ gt_all, const int* __restrict__ n_gt_all,
+                                      const int* __restrict__ img_wh, int g_max, AnchorTable tab,
+                                      int cols, int stride, int n,
+                                      const unsigned long long* __restrict__ best_gt,
+                                      unsigned char* __restrict__ can_use,
+                                      unsigned char* __restrict__ is_pos, float4* __restrict__ bbreg) {
+  const int img = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = min(n_gt_all[img], g_max);
+  if (g >= G) return;
+  const unsigned long long key = best_gt[(size_t)img * g_max + g];
+  if ((key >> 32) == 0ull) return;              // max IoU == 0 (rpn_util.py:77)
+  const int i = (int)(~(unsigned)(key & 0xffffffffull));
+  int x1, y1, x2, y2;
+  pixel_anchor(i, tab, cols, stride, x1, y1, x2, y2);
+  const float fx1 = (float)x1, fy1 = (float)y1, fx2 = (float)x2, fy2 = (float)y2;
+  const float a_area = __fmul_rn(__fsub_rn(fx2, fx1), __fsub_rn(fy2, fy1));
+  const float* gt = gt_all + (size_t)img * g_max * 4;
+  // regression target goes to the anchor's OWN best GT (rpn_util.py:90), recomputed here
+  float best = 0.f;
+  int best_g = 0;
+  for (int q = 0; q < G; ++q) {
+    const float gx1 = gt[4 * q], gy1 = gt[4 * q + 1], gx2 = gt[4 * q + 2], gy2 = gt[4 * q + 3];
+    const float v = iou_f32(fx1, fy1, fx2, fy2, a_area, gx1, gy1, gx2, gy2,
+                            __fmul_rn(__fsub_rn(gx2, gx1), __fsub_rn(gy2, gy1)));
+    if (q == 0 || v > best) { best = v; best_g = q; }
+  }
+  const int W = img_wh[2 * img], H = img_wh[2 * img + 1];
+  const bool oob = (x1 < 0) || (y1 < 0) || (x2 >= W) || (y2 >= H);
+  const size_t o = (size_t)img * n + i;
+  // several GTs may share one arg-max anchor: every writer stores identical values
+  is_pos[o] = 1;
+  can_use[o] = !oob;
+  bbreg[o] = rpn_bbreg(x1, y1, x2, y2, gt[4 * best_g], gt[4 * best_g + 1], gt[4 * best_g + 2], gt[4 * best_g + 3]);
+}
+
+__global__ void __launch_bounds__(LBL_THREADS)
+count_kernel(const unsigned char* __restrict__ can_use, const unsigned char* __restrict__ is_pos, int n,
+             int* __restrict__ counts) {
+  const int img = blockIdx.y;
+  const int i = blockIdx.x * LBL_THREADS + threadIdx.x;
+  bool p = false, q = false;
+  if (i < n) {
+    const size_t o = (size_t)img * n + i;
+    p = can_use[o] && is_pos[o];
+    q = can_use[o] && !is_pos[o];
+  }
+  const int np_ = __popc(__ballot_sync(0xffffffffu, p)), nq = __popc(__ballot_sync(0xffffffffu, q));
+  if ((threadIdx.x & 31) == 0) {
+    if (np_) atomicAdd(counts + 2 * img, np_);
+    if (nq) atomicAdd(counts + 2 * img + 1, nq);
+  }
+}
+
+// Host-drawn sampling (rpn_util.py:324-350): one CTA per image.  off_pos / off_neg hold RANKS --
+// positions among the image's usable positives / negatives in ascending anchor order, i.e. the
+// values random.sample(range(num_pos|num_neg), ...) returned -- and the anchors at those ranks get
+// can_use = 0.  Ranks are staged as bitmaps in shared memory; an ordered ballot scan over the
+// anchors recovers every anchor's rank.  Both rank sets refer to the flags as they were on entry.
+constexpr int SMP_THREADS = 1024;
+__global__ void __launch_bounds__(SMP_THREADS)
+apply_sampling_kernel(unsigned char* __restrict__ can_use_all, const unsigned char* __restrict__ is_pos_all, int n,
+                      const int* __restrict__ off_pos, const int* __restrict__ off_pos_offsets,
+                      const int* __restrict__ off_neg, const int* __restrict__ off_neg_offsets, int words) {
+  extern __shared__ unsigned smp_bits[];
+  unsigned* pos_bits = smp_bits;
+  unsigned* neg_bits = smp_bits + words;
+  __shared__ int tot_p[SMP_THREADS / 32], tot_q[SMP_THREADS / 32];
+  __shared__ int base_p, base_q;
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = off_pos ? off_pos_offsets[img] : 0, p1 = off_pos ? off_pos_offsets[img + 1] : 0;
+  const int q0 = off_neg ? off_neg_offsets[img] : 0, q1 = off_neg ? off_neg_offsets[img + 1] : 0;
+  if (p1 <= p0 && q1 <= q0) return;                 // nothing to switch off in this image (CTA-uniform)
+  for (int i = tid; i < 2 * words; i += SMP_THREADS) smp_bits[i] = 0u;
+  if (tid == 0) { base_p = 0; base_q = 0; }
+  __syncthreads();
+  for (int j = p0 + tid; j < p1; j += SMP_THREADS) {
+    const int r = off_pos[j];
+    if (r >= 0 && r < n) atomicOr(&pos_bits[r >> 5], 1u << (r & 31));
+  }
+  for (int j = q0 + tid; j < q1; j += SMP_THREADS) {
+    const int r = off_neg[j];
+    if (r >= 0 && r < n) atomicOr(&neg_bits[r >> 5], 1u << (r & 31));
+  }
+  __syncthreads();
+  unsigned char* can_use = can_use_all + (size_t)img * n;
+  const unsigned char* is_pos = is_pos_all + (size_t)img * n;
+  const unsigned below = (1u << lane) - 1u;
+  for (int start = 0; start < n; start += SMP_THREADS) {
+    const int i = start + tid;
+    bool p = false, q = false;
+    if (i < n) {
+      const bool cu = can_use[i] != 0, ip = is_pos[i] != 0;
+      p = cu && ip;
+      q = cu && !ip;
+    }
+    const unsigned bp = __ballot_sync(0xffffffffu, p), bq = __ballot_sync(0xffffffffu, q);
+    if (lane == 0) { tot_p[warp] = __popc(bp); tot_q[warp] = __popc(bq); }
+    __syncthreads();
+    int rp = base_p, rq = base_q;
+    for (int w = 0; w < warp; ++w) { rp += tot_p[w]; rq += tot_q[w]; }
+    rp += __popc(bp & below);
+    rq += __popc(bq & below);
+    if (p && ((pos_bits[rp >> 5] >> (rp & 31)) & 1u)) can_use[i] = 0;
+    if (q && ((neg_bits[rq >> 5] >> (rq & 31)) & 1u)) can_use[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+      int ap = 0, aq = 0;
+      for (int w = 0; w < SMP_THREADS / 32; ++w) { ap += tot_p[w]; aq += tot_q[w]; }
+      base_p += ap;
+      base_q += aq;
+    }
+    __syncthreads();
+  }
+}
+
+// one thread per location (y, x) of one image: writes 2A bytes + 8A floats contiguous per cell.
+__global__ void __launch_bounds__(LBL_THREADS)
+pack_rpn_kernel(const unsigned char* __restrict__ can_use, const unsigned char* __restrict__ is_pos,
+                const float* __restrict__ bbreg, int n_loc, int A, unsigned char* __restrict__ y_class,
+                float* __restrict__ y_bbreg) {
+  // flat over (image, location, 8A slots of y_bbreg); y_class handled by the first 2A slots
+  const size_t total = (size_t)gridDim.y * 0 + (size_t)n_loc * 8 * A;
+  const int img = blockIdx.y;
+  for (size_t e = (size_t)blockIdx.x * LBL_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * LBL_THREADS) {
+    const int loc = (int)(e / (8 * A)), s = (int)(e % (8 * A));
+    const size_t abase = ((size_t)img * n_loc + loc) * A;
+    float v;
+    if (s < 4 * A) {
+      const int a = s >> 2;                                   // np.repeat(sel, 4, axis=2)
+      v = (can_use[abase + a] && is_pos[abase + a]) ? 1.0f : 0.0f;
+    } else {
+      v = bbreg[abase * 4 + (s - 4 * A)];
+    }
+    y_bbreg[((size_t)img * n_loc + loc) * 8 * A + s] = v;
+    if (s < 2 * A) {
+      const unsigned char c = (s < A) ? can_use[abase + s] : is_pos[abase + s - A];
+      y_class[((size_t)img * n_loc + loc) * 2 * A + s] = c;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Detector RoI labelling: one CTA per image.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LBL_THREADS)
+label_rois_kernel(const BoxI16* __restrict__ rois_all, const int* __restrict__ n_roi_all, int n_max,
+                  const double* __restrict__ gt_all, const int* __restrict__ gt_cls_all,
+                  const int* __restrict__ n_gt_all, int g_max, int K, BoxI16* __restrict__ out_rois,
+                  int* __restrict__ out_cls, float* __restrict__ out_bbreg, int* __restrict__ out_src,
+                  int* __restrict__ out_count) {
+  __shared__ float4 s_gt[FRCNN_MAX_GT];
+  __shared__ float s_garea[FRCNN_MAX_GT];
+  __shared__ int s_warp_tot[LBL_THREADS / 32];
+  __shared__ int s_base;
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = n_roi_all ? min(n_roi_all[img], n_max) : n_max;
+  const int G = min(n_gt_all[img], g_max);
+  const double* gt64 = gt_all + (size_t)img * g_max * 4;
+  const int* gcls = gt_cls_all + (size_t)img * g_max;
+  const BoxI16* rois = rois_all + (size_t)img * n_max;
+  const int kfg = K - 1;
+  for (int g = tid; g < G; g += LBL_THREADS) {
+    const float4 b = make_float4((float)gt64[4 * g], (float)gt64[4 * g + 1], (float)gt64[4 * g + 2], (float)gt64[4 * g + 3]);
+    s_gt[g] = b;                                              // util.py:229-239: f64 -> f32 copy
+    s_garea[g] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  }
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+
+  for (int start = 0; start < n; start += LBL_THREADS) {
+    const int i = start + tid;
+    bool elig = false, pos = false;
+    int best_g = 0;
+    BoxI16 r = {0, 0, 0, 0};
+    if (i < n && G > 0) {
+      r = rois[i];
+      // int16 areas are exact integers (no wrap below 181x181 cells); widened to f32 by the add
+      const float fx1 = (float)r.x1, fy1 = (float)r.y1, fx2 = (float)r.x2, fy2 = (float)r.y2;
+      const float a_area = (float)((int)(short)((r.x2 - r.x1) * (r.y2 - r.y1)));
+      float best = 0.f;
+      for (int g = 0; g < G; ++g) {
+        const float4 b = s_gt[g];
+        const float v = iou_f32(fx1, fy1, fx2, fy2, a_area, b.x, b.y, b.z, b.w, s_garea[g]);
+        if (g == 0 || v > best) { best = v; best_g = g; }
+      }
+      elig = best >= 0.1f;                                    // det_util.py:318 (float32 compare)
+      pos = best >= 0.5f;                                     // det_util.py:321
+    }
+    // order-preserving compaction
+    const unsigned ball = __ballot_sync(0xffffffffu, elig);
+    if (lane == 0) s_warp_tot[warp] = __popc(ball);
+    __syncthreads();
+    int before = s_base;
+    for (int wv = 0; wv < warp; ++wv) before += s_warp_tot[wv];
+    const int row = before + __popc(ball & ((1u << lane) - 1u));
+    if (elig) {
+      const size_t o = (size_t)img * n_max + row;
+      out_rois[o] = r;
+      if (out_src) out_src[o] = i;
+      int* oc = out_cls + o * K;
+      float* ob = out_bbreg + o * 8 * kfg;
+      for (int c = 0; c < K; ++c) oc[c] = 0;
+      for (int c = 0; c < 8 * kfg; ++c) ob[c] = 0.f;
+      if (!pos) {
+        oc[K - 1] = 1;
+      } else {
+        const int c = gcls[best_g];
+        oc[c] = 1;
+        // det_util.py:346-352: get_reg_params(roi int16, GT float64) in float64, stored to f32,
+        // then multiplied by [10,10,5,5] in float32.
+        const double gx1 = gt64[4 * best_g], gy1 = gt64[4 * best_g + 1], gx2 = gt64[4 * best_g + 2], gy2 = gt64[4 * best_g + 3];
+        const double gcx = __ddiv_rn(__dadd_rn(gx2, gx1), 2.0), gcy = __ddiv_rn(__dadd_rn(gy2, gy1), 2.0);
+        const double gw = __dsub_rn(gx2, gx1), gh = __dsub_rn(gy2, gy1);
+        const double acx = (double)(short)(r.x2 + r.x1) / 2.0, acy = (double)(short)(r.y2 + r.y1) / 2.0;
+        const double aw = (double)(short)(r.x2 - r.x1), ah = (double)(short)(r.y2 - r.y1);
+        const float tx = (float)__ddiv_rn(__dsub_rn(gcx, acx), aw), ty = (float)__ddiv_rn(__dsub_rn(gcy, acy), ah);
+        const float tw = (float)log(__ddiv_rn(gw, aw)), th = (float)log(__ddiv_rn(gh, ah));
+        ob[4 * c + 0] = 1.f; ob[4 * c + 1] = 1.f; ob[4 * c + 2] = 1.f; ob[4 * c + 3] = 1.f;
+        float* tg = ob + 4 * kfg + 4 * c;
+        tg[0] = __fmul_rn(tx, 10.f); tg[1] = __fmul_rn(ty, 10.f); tg[2] = __fmul_rn(tw, 5.f); tg[3] = __fmul_rn(th, 5.f);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int add = 0;
+      for (int wv = 0; wv < LBL_THREADS / 32; ++wv) add += s_warp_tot[wv];
+      s_base += add;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) out_count[img] = s_base;
+}
+
+// ------------------------------------------------------------------------------------------
+int launch_label_anchors(frcnn_handle* h, cudaStream_t stream, const float* gt, const int32_t* n_gt,
+                         const int32_t* img_wh, int g_max, const AnchorTable& tab, int rows, int cols,
+                         int stride, int batch, uint8_t* can_use, uint8_t* is_pos, float* bbreg,
+                         int32_t* counts) {
+  const int n = rows * cols * tab.n;
+  void* ws = nullptr;
+  const size_t best_bytes = (size_t)batch * g_max * sizeof(unsigned long long);
+  int rc = arena_get(h, stream, best_bytes, &ws);
+  if (rc) return rc;
+  auto* best = reinterpret_cast<unsigned long long*>(ws);
+  FRCNN_CUDA(h, cudaMemsetAsync(best, 0, best_bytes, stream));
+  FRCNN_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)batch * 2 * sizeof(int), stream));
+  dim3 grid((n + LBL_THREADS - 1) / LBL_THREADS, batch);
+  label_anchors_kernel<<<grid, LBL_THREADS, 0, stream>>>(gt, n_gt, img_wh, g_max, tab, rows, cols, stride, n,
+                                                        can_use, is_pos, reinterpret_cast<float4*>(bbreg), best);
+  FRCNN_LAUNCH_CHECK(h, "label_anchors_kernel");
+  dim3 g2((g_max + 63) / 64, batch);
+  label_gt_fixup_kernel<<<g2, 64, 0, stream>>>(gt, n_gt, img_wh, g_max, tab, cols, stride, n, best, can_use,
+                                              is_pos, reinterpret_cast<float4*>(bbreg));
+  FRCNN_LAUNCH_CHECK(h, "label_gt_fixup_kernel");
+  count_kernel<<<grid, LBL_THREADS, 0, stream>>>(can_use, is_pos, n, counts);
+  FRCNN_LAUNCH_CHECK(h, "count_kernel");
+  return FRCNN_OK;
+}
+
+int launch_pack_rpn(frcnn_handle* h, cudaStream_t stream, uint8_t* can_use, const uint8_t* is_pos,
+                    const float* bbreg, const int32_t* off_pos, const int32_t* off_pos_offsets,
+                    const int32_t* off_neg, const int32_t* off_neg_offsets, int rows, int cols, int A,
+                    int batch, uint8_t* y_class, float* y_bbreg) {
+  const int n_loc = rows * cols;
+  if (off_pos || off_neg) {
+    const int n = n_loc * A;
+    const int words = (n + 31) / 32;
+    const size_t smem = (size_t)2 * words * sizeof(unsigned);
+    if (smem + 1024 > (size_t)h->max_smem_optin)
+      return fail(h, FRCNN_ERR_UNSUPPORTED, "pack_rpn_targets: too many anchors per image for the rank bitmaps%s%s");
+    if (smem > 48 * 1024)
+      FRCNN_CUDA(h, cudaFuncSetAttribute(apply_sampling_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    apply_sampling_kernel<<<batch, SMP_THREADS, smem, stream>>>(can_use, is_pos, n, off_pos, off_pos_offsets, off_neg,
+                                                               off_neg_offsets, words);
+    FRCNN_LAUNCH_CHECK(h, "apply_sampling_kernel");
+  }
+  const size_t per_img = (size_t)n_loc * 8 * A;
+  int gx = (int)((per_img + LBL_THREADS - 1) / LBL_THREADS);
+  if (gx > 4096) gx = 4096;
+  pack_rpn_kernel<<<dim3(gx, batch), LBL_THREADS, 0, stream>>>(can_use, is_pos, bbreg, n_loc, A, y_class, y_bbreg);
+  FRCNN_LAUNCH_CHECK(h, "pack_rpn_kernel");
+  return FRCNN_OK;
+}
+
+int launch_label_rois(frcnn_handle* h, cudaStream_t stream, const int16_t* rois, const int32_t* n_roi,
+                      int n_max, const double* gt, const int32_t* gt_cls, const int32_t* n_gt, int g_max,
+                      int K, int batch, int16_t* out_rois, int32_t* out_cls, float* out_bbreg,
+                      int32_t* out_src, int32_t* out_count) {
+  label_rois_kernel<<<batch, LBL_THREADS, 0, stream>>>(reinterpret_cast<const BoxI16*>(rois), n_roi, n_max, gt,
+                                                      gt_cls, n_gt, g_max, K,
+                                                      reinterpret_cast<BoxI16*>(out_rois), out_cls, out_bbreg,
+                                                      out_src, out_count);
+  FRCNN_LAUNCH_CHECK(h, "label_rois_kernel");
+  return FRCNN_OK;
+}
+
+}  // namespace frcnn

@@ -1,0 +1,343 @@
+// K-b: greedy NMS.  One CTA per image (int16 RPN boxes) or per segment (float64 per-class
+// boxes); the whole problem lives in shared memory.
+//
+// Algorithm (work-efficient form of the bitmask NMS):
+//   1. order: visit candidates by (score desc, position desc) -- the order
+//      `np.argsort(probs, kind='stable')` consumed from the back gives (det_util.py:231-236).
+//      If the scores already arrive strictly descending (the output of K-a) the order is the
+//      identity and the box array is pulled into shared memory with one 1-D TMA bulk copy
+//      (cp.async.bulk + mbarrier); otherwise 64-bit keys are bitonic-sorted in shared memory
+//      and the boxes are gathered into the same buffer.
+//   2. sweep in tiles of 64 candidates: (a) each candidate of the tile is tested against the
+//      kept list (shared memory, broadcast reads), warp ballots build the 64-bit
+//      "suppressed by kept" mask; (b) the 64x64 intra-tile IoU matrix is reduced to 64-bit row
+//      masks; (c) one thread resolves the tile serially over set bits only and appends the
+//      survivors to the kept list.  Only kept x candidate pairs are ever tested
+//      (<= n*max_boxes instead of n^2/2) and the sweep stops at max_boxes (det_util.py:253-254).
+//
+// Predicate (det_util.py:243-251): areas with the +1 convention, ratio = inter/union in
+// float64, candidate survives iff ratio <= thresh.  For int16 boxes inter and union are exact
+// integers; a float32 band test decides the clear cases and only |inter - t*union| tiny falls
+// through to the IEEE float64 division, so the decision is identical to numpy's.
+#include "common.cuh"
+
+namespace frcnn {
+
+constexpr int NMS_THREADS = 512;
+constexpr int NMS_TILE = 64;
+
+struct __align__(8) BoxI16 { short x1, y1, x2, y2; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// exact int16 pair test; a = kept box, b = candidate.  returns true if b is suppressed.
+__device__ __forceinline__ bool suppressed_i16(int ax1, int ay1, int ax2, int ay2, int a_area,
+                                               int bx1, int by1, int bx2, int by2, int b_area,
+                                               float t_f, double t, bool zero_survives) {
+  const int iw = min(ax2, bx2) - max(ax1, bx1) + 1;
+  const int ih = min(ay2, by2) - max(ay1, by1) + 1;
+  const int inter = (iw > 0 && ih > 0) ? iw * ih : 0;
+  const int uni = a_area + b_area - inter;
+  if (uni > 0) {
+    if (inter == 0) return !zero_survives;
+    const float fi = (float)inter, fu = (float)uni;
+    const float d = __fmaf_rn(-t_f, fu, fi);               // inter - t*union, ~1e-7 relative
+    const float band = 1e-4f * fu;
+    if (d > band) return true;
+    if (d < -band) return false;
+  }
+  const double ratio = __ddiv_rn((double)inter, (double)uni);   // IEEE, same as numpy true_divide
+  return !(ratio <= t);
+}
+
+// Dynamic shared memory layout (bytes):
+//   [0, buf_bytes)            sort keys (u64) then, in place, boxes in visit order (8 B each)
+//   kept boxes int4[max_keep] ; kept area int[max_keep] ; kept slot (visit rank) int[max_keep]
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ scores_all,
+               const int* __restrict__ n_all, int n_max, double thresh, int max_boxes, int max_keep,
+               int buf_elems, int* __restrict__ order_all, int* __restrict__ keep_index,
+               int* __restrict__ keep_count, BoxI16* __restrict__ keep_boxes,
+               float* __restrict__ keep_scores) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem);
+  int4* kept_box = reinterpret_cast<int4*>(smem + (size_t)buf_elems * 8);
+  int* kept_area = reinterpret_cast<int*>(kept_box + max_keep);
+  int* kept_slot = kept_area + max_keep;
+
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ unsigned long long row_mask[NMS_TILE];
+  __shared__ unsigned sup_part[NMS_THREADS / 32];
+  __shared__ unsigned long long s_keepbits;
+  __shared__ int s_unsorted, s_nkept, s_stop;
+
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = n_all ? min(n_all[img], n_max) : n_max;
+  const BoxI16* boxes = boxes_all + (size_t)img * n_max;
+  const float* scores = scores_all + (size_t)img * n_max;
+  int* order = order_all + (size_t)img * n_max;
+
+  if (tid == 0) { s_unsorted = 0; s_nkept = 0; s_stop = 0; }
+  __syncthreads();
+
+  // ---- 1. visit order --------------------------------------------------------------------
+  int bad = 0;
+  for (int i = tid; i + 1 < n; i += NMS_THREADS) bad |= !(scores[i] > scores[i + 1]);
+  if (__any_sync(0xffffffffu, bad) && lane == 0) s_unsorted = 1;
+  __syncthreads();
+  const bool unsorted = s_unsorted != 0;
+
+  if (!unsorted) {
+    // identity order: 1-D TMA bulk copy of the contiguous box rows into shared memory
+    const uint32_t bytes = (uint32_t)n * 8u;
+    const bool tma_ok = (bytes % 16u == 0) && ((reinterpret_cast<uintptr_t>(boxes) & 15u) == 0) && n > 0;
+    if (tma_ok) {
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(buf)), "l"(boxes), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+      }
+      // everyone waits on phase 0
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+      }
+    } else {
+      for (int i = tid; i < n; i += NMS_THREADS) buf[i] = reinterpret_cast<const unsigned long long*>(boxes)[i];
+    }
+    __syncthreads();
+  } else {
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = tid; i < m; i += NMS_THREADS)
+      buf[i] = (i < n) ? (((unsigned long long)mono_key(scores[i]) << 32) | (unsigned)i) : 0ull;
+    // padding keys are 0: mono_key() of any real score is >= 1, so padding sorts last
+    bitonic_sort_desc(buf, m);
+    for (int base = 0; base < n; base += NMS_THREADS) {
+      const int i = base + tid;
+      unsigned long long b = 0ull;
+      int pos = 0;
+      if (i < n) {   // slot i is read and rewritten by the same thread: no hazard
+        pos = (int)(unsigned)(buf[i] & 0xffffffffull);
+        b = reinterpret_cast<const unsigned long long*>(boxes)[pos];
+        order[i] = pos;
+        buf[i] = b;
+      }
+    }
+    __syncthreads();
+  }
+  const BoxI16* sorted = reinterpret_cast<const BoxI16*>(buf);
+
+  // ---- 2. tiled sweep --------------------------------------------------------------------
+  const float t_f = (float)thresh;
+  const bool zero_survives = (0.0 <= thresh);
+  const int cand = tid & (NMS_TILE - 1);
+  const int slice = tid >> 6;                       // NMS_THREADS / NMS_TILE = 8 slices of the kept list
+  constexpr int SLICES = NMS_THREADS / NMS_TILE;
+
+  for (int base = 0; base < n; base += NMS_TILE) {
+    const int tile_n = min(NMS_TILE, n - base);
+    const int nkept = s_nkept;
+    // (a) candidate vs kept list
+    BoxI16 cb = {0, 0, 0, 0};
+    if (cand < tile_n) cb = sorted[base + cand];
+    const int bx1 = cb.x1, by1 = cb.y1, bx2 = cb.x2, by2 = cb.y2;
+    const int b_area = (bx2 - bx1 + 1) * (by2 - by1 + 1);
+    bool sup = false;
+    for (int j = slice; j < nkept; j += SLICES) {
+      const int4 kb = kept_box[j];
+      sup |= suppressed_i16(kb.x, kb.y, kb.z, kb.w, kept_area[j], bx1, by1, bx2, by2, b_area, t_f, thresh, zero_survives);
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, sup);
+    if (lane == 0) sup_part[warp] = ball;
+    // (b) intra-tile row masks: thread -> row i = tid/8, eight columns j = (tid%8)*8 ..
+    {
+      const int i = tid >> 3, j0 = (tid & 7) * 8;
+      unsigned lo = 0, hi = 0;
+      if (i < tile_n) {
+        const BoxI16 a = sorted[base + i];
+        const int a_area = (a.x2 - a.x1 + 1) * (a.y2 - a.y1 + 1);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = j0 + jj;
+          if (j > i && j < tile_n) {
+            const BoxI16 c = sorted[base + j];
+            const int c_area = (c.x2 - c.x1 + 1) * (c.y2 - c.y1 + 1);
+            if (suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives)) {
+              if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+            }
+          }
+        }
+      }
+      const unsigned gmask = 0xffu << (lane & 24);
+      lo = __reduce_or_sync(gmask, lo);
+      hi = __reduce_or_sync(gmask, hi);
+      if ((tid & 7) == 0) row_mask[i] = ((unsigned long long)hi << 32) | lo;
+    }
+    __syncthreads();
+    // (c) serial resolve over live bits only
+    if (tid == 0) {
+      unsigned long long supk = 0ull;
+#pragma unroll
+      for (int s = 0; s < SLICES; ++s) {
+        supk |= (unsigned long long)sup_part[2 * s] | ((unsigned long long)sup_part[2 * s + 1] << 32);
+      }
+      unsigned long long alive = ~supk;
+      if (tile_n < 64) alive &= (1ull << tile_n) - 1ull;
+      unsigned long long keepbits = 0ull;
+      int room = max_boxes - nkept;
+      while (alive && room > 0) {
+        const int i = __ffsll((long long)alive) - 1;
+        keepbits |= 1ull << i;
+        alive &= ~row_mask[i];
+        alive &= ~(1ull << i);
+        --room;
+      }
+      s_keepbits = keepbits;
+      s_nkept = nkept + __popcll(keepbits);
+      if (room == 0) s_stop = 1;
+    }
+    __syncthreads();
+    const unsigned long long keepbits = s_keepbits;
+    if (tid < NMS_TILE && ((keepbits >> tid) & 1ull)) {
+      const int slot = nkept + __popcll(keepbits & ((1ull << tid) - 1ull));
+      kept_box[slot] = make_int4(bx1, by1, bx2, by2);      // tid < 64 => cand == tid
+      kept_area[slot] = b_area;
+      kept_slot[slot] = base + tid;
+    }
+    __syncthreads();
+    if (s_stop) break;
+  }
+
+  // ---- 3. outputs ------------------------------------------------------------------------
+  const int total = s_nkept;
+  for (int r = tid; r < max_boxes; r += NMS_THREADS) {
+    const size_t o = (size_t)img * max_boxes + r;
+    if (r < total) {
+      const int rank = kept_slot[r];
+      const int pos = unsorted ? order[rank] : rank;
+      keep_index[o] = pos;
+      if (keep_boxes) keep_boxes[o] = sorted[rank];
+      if (keep_scores) keep_scores[o] = scores[pos];
+    } else {
+      keep_index[o] = -1;
+      if (keep_boxes) keep_boxes[o] = BoxI16{0, 0, 0, 0};
+      if (keep_scores) keep_scores[o] = 0.0f;
+    }
+  }
+  if (tid == 0) keep_count[img] = total;
+}
+
+int launch_nms_i16(frcnn_handle* h, cudaStream_t stream, const int16_t* boxes, const float* scores,
+                   const int32_t* n, int n_max, int batch, double thresh, int max_boxes,
+                   int32_t* keep_index, int32_t* keep_count, int16_t* keep_boxes, float* keep_scores) {
+  if (n_max > FRCNN_NMS_MAX_SORTED)
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "nms_i16: n_max exceeds FRCNN_NMS_MAX_SORTED%s%s");
+  // The sort path needs a power-of-two buffer; above FRCNN_NMS_MAX_UNSORTED only pre-sorted input fits.
+  int pow2 = 1;
+  while (pow2 < n_max) pow2 <<= 1;
+  const int buf_elems = (n_max <= FRCNN_NMS_MAX_UNSORTED) ? pow2 : n_max;
+  const int max_keep = max_boxes < n_max ? max_boxes : n_max;
+  const size_t smem = (size_t)buf_elems * 8 + (size_t)max_keep * (16 + 4 + 4) + 16;
+  if (smem + 2048 > (size_t)h->max_smem_optin)
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "nms_i16: n_max/max_boxes need more shared memory than one SM has%s%s");
+  void* ws = nullptr;
+  int rc = arena_get(h, stream, (size_t)batch * n_max * sizeof(int), &ws);
+  if (rc) return rc;
+  FRCNN_CUDA(h, cudaFuncSetAttribute(nms_i16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_i16_kernel<<<batch, NMS_THREADS, smem, stream>>>(
+      reinterpret_cast<const BoxI16*>(boxes), scores, n, n_max, thresh, max_boxes, max_keep, buf_elems,
+      reinterpret_cast<int*>(ws), keep_index, keep_count, reinterpret_cast<BoxI16*>(keep_boxes), keep_scores);
+  FRCNN_LAUNCH_CHECK(h, "nms_i16_kernel");
+  return FRCNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// float64 segmented NMS (per-class stage, voc_dets.py:72-76).  All arithmetic in IEEE double,
+// no FMA contraction (explicit _rn intrinsics), same expression order as det_util.py:230-249.
+// ------------------------------------------------------------------------------------------
+constexpr int NMS64_THREADS = 256;
+
+__device__ __forceinline__ bool suppressed_f64(const double4& a, double a_area, const double4& b,
+                                               double b_area, double t) {
+  const double iw = fmax(0.0, __dadd_rn(__dsub_rn(fmin(a.z, b.z), fmax(a.x, b.x)), 1.0));
+  const double ih = fmax(0.0, __dadd_rn(__dsub_rn(fmin(a.w, b.w), fmax(a.y, b.y)), 1.0));
+  const double inter = __dmul_rn(iw, ih);
+  const double uni = __dsub_rn(__dadd_rn(a_area, b_area), inter);
+  return !(__ddiv_rn(inter, uni) <= t);
+}
+
+// Dynamic smem: keys u64[pow2] | sorted boxes double4[n] | area double[n] | alive flags
+// Simple form: candidates are visited one at a time by the whole CTA (segments are small:
+// <= 320 rows in the reference's post-processing), each kept box clears later candidates.
+__global__ void __launch_bounds__(NMS64_THREADS)
+nms_f64_kernel(const double* __restrict__ boxes_all, const float* __restrict__ scores_all,
+               const int* __restrict__ seg_offsets, int max_seg_len, int pow2, double thresh,
+               int max_boxes, int out_stride, int* __restrict__ keep_index, int* __restrict__ keep_count) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+  double4* sb = reinterpret_cast<double4*>(smem + (size_t)pow2 * 8);
+  double* area = reinterpret_cast<double*>(sb + max_seg_len);
+  unsigned char* dead = reinterpret_cast<unsigned char*>(area + max_seg_len);
+
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  const int start = seg_offsets[seg];
+  const int n = min(seg_offsets[seg + 1] - start, max_seg_len);
+  const double* boxes = boxes_all + (size_t)start * 4;
+  const float* scores = scores_all + start;
+
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int i = tid; i < m; i += NMS64_THREADS)
+    keys[i] = (i < n) ? (((unsigned long long)mono_key(scores[i]) << 32) | (unsigned)i) : 0ull;
+  bitonic_sort_desc(keys, m);
+  for (int i = tid; i < n; i += NMS64_THREADS) {
+    const int pos = (int)(unsigned)(keys[i] & 0xffffffffull);
+    const double4 b = make_double4(boxes[4 * pos], boxes[4 * pos + 1], boxes[4 * pos + 2], boxes[4 * pos + 3]);
+    sb[i] = b;
+    area[i] = __dmul_rn(__dadd_rn(__dsub_rn(b.z, b.x), 1.0), __dadd_rn(__dsub_rn(b.w, b.y), 1.0));
+    dead[i] = 0;
+  }
+  __syncthreads();
+
+  int cur = 0, kept = 0;
+  while (true) {
+    // next live candidate (all threads scan the same flags -> uniform result)
+    while (cur < n && dead[cur]) ++cur;
+    if (cur >= n) break;
+    if (tid == 0) keep_index[(size_t)seg * out_stride + kept] = (int)(unsigned)(keys[cur] & 0xffffffffull);
+    ++kept;
+    if (kept >= max_boxes) break;
+    const double4 a = sb[cur];
+    const double a_area = area[cur];
+    for (int j = cur + 1 + tid; j < n; j += NMS64_THREADS)
+      if (!dead[j] && suppressed_f64(a, a_area, sb[j], area[j], thresh)) dead[j] = 1;
+    ++cur;
+    __syncthreads();
+  }
+  for (int r = kept + tid; r < out_stride; r += NMS64_THREADS) keep_index[(size_t)seg * out_stride + r] = -1;
+  if (tid == 0) keep_count[seg] = kept;
+}
+
+int launch_nms_f64(frcnn_handle* h, cudaStream_t stream, const double* boxes, const float* scores,
+                   const int32_t* seg_offsets, int n_seg, int max_seg_len, double thresh, int max_boxes,
+                   int out_stride, int32_t* keep_index, int32_t* keep_count) {
+  if (max_seg_len > FRCNN_NMS_F64_MAX)
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "nms_f64: segment longer than FRCNN_NMS_F64_MAX%s%s");
+  int pow2 = 4;   // >= 4 keeps the double4 array behind the keys 32-byte aligned
+  while (pow2 < max_seg_len) pow2 <<= 1;
+  const size_t smem = (size_t)pow2 * 8 + (size_t)max_seg_len * (32 + 8 + 1) + 64;
+  FRCNN_CUDA(h, cudaFuncSetAttribute(nms_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_f64_kernel<<<n_seg, NMS64_THREADS, smem, stream>>>(boxes, scores, seg_offsets, max_seg_len, pow2,
+                                                        thresh, max_boxes, out_stride, keep_index, keep_count);
+  FRCNN_LAUNCH_CHECK(h, "nms_f64_kernel");
+  return FRCNN_OK;
+}
+
+}  // namespace frcnn

@@ -1,0 +1,267 @@
+"""Device-resident functional API: torch CUDA tensors in, torch CUDA tensors out.
+
+One function per C-ABI entry point (include/frcnn_b200.h).  Everything is enqueued on torch's
+current stream and nothing here synchronises; the numpy drop-in modules (`det_util`, `rpn_util`,
+`util`, `custom_layers`, `voc_dets`) sit on top of these.  A leading batch dimension = independent
+images.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .runtime import get_context, ptr
+
+_ROI_DTYPES = {torch.int16: _lib.ROI_I16, torch.int32: _lib.ROI_I32, torch.float32: _lib.ROI_F32}
+_MODES = {"resize": _lib.ROI_RESIZE, "max": _lib.ROI_MAX}
+
+
+def _chk(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dimensions, got shape %s" % (name, ndim, tuple(t.shape)))
+    return t.contiguous()
+
+
+def decode_topk(regr, cls, anchor_dims, stride, k, want_dense=False):
+    """K-a.  regr (B,R,C,4A) f32, cls (B,R,C,A) f32 -> boxes (B,k,4) i16, scores (B,k) f32,
+    index (B,k) i32, count (B,) i32 [, dense (B,R*C*A,4) f32].  det_util.py:63-76,145-155,370-380."""
+    regr, cls = _chk(regr, torch.float32, "regr", 4), _chk(cls, torch.float32, "cls", 4)
+    ctx = get_context(regr.device)
+    b, rows, cols, a = cls.shape
+    if regr.shape != (b, rows, cols, 4 * a):
+        raise ValueError("regr shape %s does not match cls shape %s" % (tuple(regr.shape), tuple(cls.shape)))
+    anc, n_anc = ctx.anchors(anchor_dims)
+    if n_anc != a:
+        raise ValueError("cls has %d anchors per cell, anchor_dims has %d" % (a, n_anc))
+    k = int(min(k, rows * cols * a))
+    boxes, scores = ctx.empty((b, k, 4), torch.int16), ctx.empty((b, k), torch.float32)
+    index, count = ctx.empty((b, k), torch.int32), ctx.empty((b,), torch.int32)
+    dense = ctx.empty((b, rows * cols * a, 4), torch.float32) if want_dense else None
+    ctx.call("frcnn_decode_topk", ptr(regr), ptr(cls), anc, rows, cols, a, int(stride), k, b, ptr(boxes),
+             ptr(scores), ptr(index), ptr(count), ptr(dense))
+    return (boxes, scores, index, count, dense) if want_dense else (boxes, scores, index, count)
+
+
+def nms_i16(boxes, scores, n=None, overlap_thresh=0.7, max_boxes=300):
+    """K-b.  boxes (B,n_max,4) i16, scores (B,n_max) f32, n (B,) i32 or None ->
+    keep_index (B,max_boxes) i32 (-1 padded), keep_count (B,), keep_boxes, keep_scores.
+    det_util.py:209-256."""
+    boxes, scores = _chk(boxes, torch.int16, "boxes", 3), _chk(scores, torch.float32, "scores", 2)
+    ctx = get_context(boxes.device)
+    b, n_max, _ = boxes.shape
+    if n is not None:
+        n = _chk(n, torch.int32, "n", 1)
+    max_boxes = int(max_boxes)
+    ki, kc = ctx.empty((b, max_boxes), torch.int32), ctx.empty((b,), torch.int32)
+    kb, ks = ctx.empty((b, max_boxes, 4), torch.int16), ctx.empty((b, max_boxes), torch.float32)
+    ctx.call("frcnn_nms_i16", ptr(boxes), ptr(scores), ptr(n), n_max, b, float(overlap_thresh), max_boxes,
+             ptr(ki), ptr(kc), ptr(kb), ptr(ks))
+    return ki, kc, kb, ks
+
+
+def nms_f64(boxes, scores, seg_offsets, max_seg_len, overlap_thresh=0.5, max_boxes=2000):
+    """K-b'.  boxes (T,4) f64, scores (T,) f32, seg_offsets (S+1,) i32 -> keep_index (S,stride) i32
+    relative to the segment start, keep_count (S,).  det_util.py:209-256 as called at voc_dets.py:76."""
+    boxes, scores = _chk(boxes, torch.float64, "boxes", 2), _chk(scores, torch.float32, "scores", 1)
+    seg_offsets = _chk(seg_offsets, torch.int32, "seg_offsets", 1)
+    ctx = get_context(boxes.device)
+    n_seg = seg_offsets.numel() - 1
+    out_stride = int(min(max_boxes, max_seg_len))
+    ki, kc = ctx.empty((n_seg, out_stride), torch.int32), ctx.empty((n_seg,), torch.int32)
+    ctx.call("frcnn_nms_f64", ptr(boxes), ptr(scores), ptr(seg_offsets), n_seg, int(max_seg_len),
+             float(overlap_thresh), int(max_boxes), out_stride, ptr(ki), ptr(kc))
+    return ki, kc
+
+
+def proposals(regr, cls, anchor_dims, stride, k, overlap_thresh=0.7, max_boxes=300):
+    """K-a -> K-b fused on the device.  Returns rois (B,max_boxes,4) i16, scores (B,max_boxes) f32,
+    count (B,) i32.  det_util.py:63-77 (k=12000, 2000) / :136-158 (k=8000, 300)."""
+    regr, cls = _chk(regr, torch.float32, "regr", 4), _chk(cls, torch.float32, "cls", 4)
+    ctx = get_context(regr.device)
+    b, rows, cols, a = cls.shape
+    if regr.shape != (b, rows, cols, 4 * a):
+        raise ValueError("regr shape %s does not match cls shape %s" % (tuple(regr.shape), tuple(cls.shape)))
+    anc, n_anc = ctx.anchors(anchor_dims)
+    if n_anc != a:
+        raise ValueError("cls has %d anchors per cell, anchor_dims has %d" % (a, n_anc))
+    max_boxes = int(max_boxes)
+    rois, scores = ctx.empty((b, max_boxes, 4), torch.int16), ctx.empty((b, max_boxes), torch.float32)
+    count = ctx.empty((b,), torch.int32)
+    ctx.call("frcnn_proposals", ptr(regr), ptr(cls), anc, rows, cols, a, int(stride), int(k), float(overlap_thresh),
+             max_boxes, b, ptr(rois), ptr(scores), ptr(count))
+    return rois, scores, count
+
+
+def label_anchors(gt, n_gt, img_wh, rows, cols, anchor_dims, stride):
+    """K-c.  gt (B,Gmax,4) f32 pixel corners, n_gt (B,) i32, img_wh (B,2) i32 (width,height) ->
+    can_use (B,N) u8, is_pos (B,N) u8, bbreg (B,N,4) f32, counts (B,2) i32.  rpn_util.py:54-103."""
+    gt, n_gt = _chk(gt, torch.float32, "gt", 3), _chk(n_gt, torch.int32, "n_gt", 1)
+    img_wh = _chk(img_wh, torch.int32, "img_wh", 2)
+    ctx = get_context(gt.device)
+    b, g_max, _ = gt.shape
+    anc, a = ctx.anchors(anchor_dims)
+    n = rows * cols * a
+    can_use, is_pos = ctx.empty((b, n), torch.uint8), ctx.empty((b, n), torch.uint8)
+    bbreg, counts = ctx.empty((b, n, 4), torch.float32), ctx.empty((b, 2), torch.int32)
+    ctx.call("frcnn_label_anchors", ptr(gt), ptr(n_gt), ptr(img_wh), g_max, int(rows), int(cols), a, anc, int(stride),
+             b, ptr(can_use), ptr(is_pos), ptr(bbreg), ptr(counts))
+    return can_use, is_pos, bbreg, counts
+
+
+def pack_rpn_targets(can_use, is_pos, bbreg, rows, cols, n_anchors, off_pos=None, off_neg=None):
+    """T6/T7.  off_pos / off_neg = (ranks (T,) i32, offsets (B+1,) i32) of the host-drawn
+    random.sample switch-offs (rpn_util.py:324-350) or None.  Clears can_use at those ranks IN
+    PLACE (can_use must be contiguous), then packs y_class (B,R,C,2A) u8 and y_bbreg (B,R,C,8A)
+    f32 (rpn_util.py:124-140)."""
+    is_pos, bbreg = _chk(is_pos, torch.uint8, "is_pos", 2), _chk(bbreg, torch.float32, "bbreg", 3)
+    if not can_use.is_contiguous():
+        raise ValueError("can_use is updated in place and must be contiguous")
+    can_use = _chk(can_use, torch.uint8, "can_use", 2)
+    ctx = get_context(can_use.device)
+    b = can_use.shape[0]
+    args = []
+    for pair, name in ((off_pos, "off_pos"), (off_neg, "off_neg")):
+        if pair is None or pair[0].numel() == 0:
+            args += [None, None]
+            continue
+        ranks, offs = _chk(pair[0], torch.int32, name, 1), _chk(pair[1], torch.int32, name + " offsets", 1)
+        if offs.numel() != b + 1:
+            raise ValueError("%s offsets must have batch+1 entries" % name)
+        args += [ptr(ranks), ptr(offs)]
+    y_class = ctx.empty((b, rows, cols, 2 * n_anchors), torch.uint8)
+    y_bbreg = ctx.empty((b, rows, cols, 8 * n_anchors), torch.float32)
+    ctx.call("frcnn_pack_rpn_targets", ptr(can_use), ptr(is_pos), ptr(bbreg), *args, int(rows), int(cols),
+             int(n_anchors), b, ptr(y_class), ptr(y_bbreg))
+    return y_class, y_bbreg
+
+
+def label_rois(rois, gt, gt_cls, n_gt, n_classes, n_roi=None):
+    """K-c'.  rois (B,n_max,4) i16, gt (B,Gmax,4) f64 feature units, gt_cls (B,Gmax) i32, n_gt (B,) ->
+    out_rois (B,n_max,4) i16, y_class (B,n_max,K) i32, y_transform (B,n_max,8(K-1)) f32,
+    src (B,n_max) i32, count (B,) i32 (rows >= count are undefined).  det_util.py:310-366."""
+    rois = _chk(rois, torch.int16, "rois", 3)
+    gt, gt_cls = _chk(gt, torch.float64, "gt", 3), _chk(gt_cls, torch.int32, "gt_cls", 2)
+    n_gt = _chk(n_gt, torch.int32, "n_gt", 1)
+    if n_roi is not None:
+        n_roi = _chk(n_roi, torch.int32, "n_roi", 1)
+    ctx = get_context(rois.device)
+    b, n_max, _ = rois.shape
+    g_max, k = gt.shape[1], int(n_classes)
+    out_rois, out_cls = ctx.empty((b, n_max, 4), torch.int16), ctx.empty((b, n_max, k), torch.int32)
+    out_bbreg = ctx.empty((b, n_max, 8 * (k - 1)), torch.float32)
+    src, count = ctx.empty((b, n_max), torch.int32), ctx.empty((b,), torch.int32)
+    ctx.call("frcnn_label_rois", ptr(rois), ptr(n_roi), n_max, ptr(gt), ptr(gt_cls), ptr(n_gt), g_max, k, b,
+             ptr(out_rois), ptr(out_cls), ptr(out_bbreg), ptr(src), ptr(count))
+    return out_rois, out_cls, out_bbreg, src, count
+
+
+def roi_forward(feat, rois, pool, mode="resize"):
+    """K-d forward.  feat (B,H,W,C) f32 channels-last, rois (B,N,4) i16/i32/f32 ->
+    out (B,N,P,P,C) f32 [, argmax (B,N,P,P,C) i32 in max mode].  custom_layers.py:35-56."""
+    feat = _chk(feat, torch.float32, "feat", 4)
+    if rois.dtype not in _ROI_DTYPES:
+        raise TypeError("rois must be int16, int32 or float32")
+    rois = _chk(rois, rois.dtype, "rois", 3)
+    ctx = get_context(feat.device)
+    b, h, w, c = feat.shape
+    n, p = rois.shape[1], int(pool)
+    out = ctx.empty((b, n, p, p, c), torch.float32)
+    argmax = ctx.empty((b, n, p, p, c), torch.int32) if mode == "max" else None
+    ctx.call("frcnn_roi_fwd", _MODES[mode], ptr(feat), h, w, c, ptr(rois), _ROI_DTYPES[rois.dtype], n, p, b,
+             ptr(out), ptr(argmax))
+    return (out, argmax) if mode == "max" else out
+
+
+def roi_backward(grad_out, rois, feat_shape, mode="resize", argmax=None):
+    """K-d backward.  grad_out (B,N,P,P,C) f32 -> grad_feat (B,H,W,C) f32 (atomic-free)."""
+    grad_out = _chk(grad_out, torch.float32, "grad_out", 5)
+    rois = _chk(rois, rois.dtype, "rois", 3)
+    ctx = get_context(grad_out.device)
+    b, h, w, c = feat_shape
+    n, p = grad_out.shape[1], grad_out.shape[2]
+    if mode == "max":
+        argmax = _chk(argmax, torch.int32, "argmax", 5)
+    gfeat = ctx.empty((b, h, w, c), torch.float32)
+    ctx.call("frcnn_roi_bwd", _MODES[mode], ptr(grad_out), ptr(rois), _ROI_DTYPES[rois.dtype],
+             ptr(argmax) if mode == "max" else None, h, w, c, n, p, b, ptr(gfeat))
+    return gfeat
+
+
+def det_postprocess(rois, out_cls, out_reg, resize_ratio, bg_index, stride=16, det_threshold=0.0, nms_thresh=0.5,
+                    max_boxes=2000):
+    """K-e.  rois (B,M,4) i16, out_cls (B,M,K) f32, out_reg (B,M,4(K-1)) f32, resize_ratio (B,) f64 ->
+    det_boxes (B,M,4) i32, det_probs (B,M) f32, det_cls (B,M) i32, det_count (B,) i32.
+    voc_dets.py:51-86."""
+    rois = _chk(rois, torch.int16, "rois", 3)
+    out_cls, out_reg = _chk(out_cls, torch.float32, "out_cls", 3), _chk(out_reg, torch.float32, "out_reg", 3)
+    resize_ratio = _chk(resize_ratio, torch.float64, "resize_ratio", 1)
+    ctx = get_context(rois.device)
+    b, m, _ = rois.shape
+    k = out_cls.shape[2]
+    if out_reg.shape != (b, m, 4 * (k - 1)):
+        raise ValueError("out_reg must be (B, M, 4*(K-1))")
+    boxes, probs = ctx.empty((b, m, 4), torch.int32), ctx.empty((b, m), torch.float32)
+    cls, count = ctx.empty((b, m), torch.int32), ctx.empty((b,), torch.int32)
+    ctx.call("frcnn_det_postprocess", ptr(rois), ptr(out_cls), ptr(out_reg), ptr(resize_ratio), m, k, int(bg_index),
+             int(stride), float(det_threshold), float(nms_thresh), int(max_boxes), b, ptr(boxes), ptr(probs),
+             ptr(cls), ptr(count))
+    return boxes, probs, cls, count
+
+
+def cross_ious(boxes, gt):
+    """util.cross_ious (util.py:146-177).  boxes (N,4) i16 or f32, gt (G,4) f32 -> (N,G) f32."""
+    if boxes.dtype not in (torch.int16, torch.float32):
+        raise TypeError("boxes must be int16 or float32")
+    boxes, gt = _chk(boxes, boxes.dtype, "boxes", 2), _chk(gt, torch.float32, "gt", 2)
+    ctx = get_context(boxes.device)
+    out = ctx.empty((boxes.shape[0], gt.shape[0]), torch.float32)
+    ctx.call("frcnn_cross_ious", ptr(boxes), _ROI_DTYPES[boxes.dtype], boxes.shape[0], ptr(gt), gt.shape[0], ptr(out))
+    return out
+
+
+def box_transform_(boxes, deltas=None, sanitize=None):
+    """In place: util.transform_np_inplace (deltas given) and/or det_util._sanitize_boxes_inplace
+    (sanitize=(cols, rows)).  boxes (N,4) f32."""
+    boxes = _chk(boxes, torch.float32, "boxes", 2)
+    if deltas is not None:
+        deltas = _chk(deltas, torch.float32, "deltas", 2)
+    cols, rows = sanitize if sanitize is not None else (0, 0)
+    get_context(boxes.device).call("frcnn_box_transform", ptr(boxes), ptr(deltas), boxes.shape[0],
+                                   1 if deltas is not None else 0, int(cols), int(rows))
+    return boxes
+
+
+def anchor_grid(anchor_dims, rows, cols, stride=1, pixel_space=False, device=None):
+    """(rows*cols*A, 4) f32 anchors; feature space (det_util.py:162-175) or pixel space
+    (rpn_util.py:276-298)."""
+    ctx = get_context(device)
+    anc, a = ctx.anchors(anchor_dims)
+    out = ctx.empty((rows * cols * a, 4), torch.float32)
+    ctx.call("frcnn_anchor_grid", anc, a, int(rows), int(cols), int(stride), 1 if pixel_space else 0, ptr(out))
+    return out
+
+
+def valid_boxes(boxes):
+    """det_util._get_valid_box_idxs (det_util.py:196-205): index (N,) i32 + count (1,) i32."""
+    boxes = _chk(boxes, torch.float32, "boxes", 2)
+    ctx = get_context(boxes.device)
+    index, count = ctx.empty((max(boxes.shape[0], 1),), torch.int32), ctx.empty((1,), torch.int32)
+    ctx.call("frcnn_valid_boxes", ptr(boxes), boxes.shape[0], ptr(index), ptr(count))
+    return index, count
+
+
+def pad_rois(rois, count, group=64):
+    """voc_dets.py:37-46 on the device: rois (B,n_max,4) i16 + count (B,) -> padded (B,M,4) i16 with
+    M = n_max rounded up to `group` (last detector batch filled with copies of its first RoI, unused
+    rows = empty box) and rows (B,) i32 = count rounded up."""
+    rois, count = _chk(rois, torch.int16, "rois", 3), _chk(count, torch.int32, "count", 1)
+    ctx = get_context(rois.device)
+    b, n_max, _ = rois.shape
+    m = -(-n_max // group) * group
+    out, rows = ctx.empty((b, m, 4), torch.int16), ctx.empty((b,), torch.int32)
+    ctx.call("frcnn_pad_rois", ptr(rois), ptr(count), n_max, int(group), m, b, ptr(out), ptr(rows))
+    return out, rows

@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing: images are independent on this path, so work is sharded by image and
+there is NO collective on the hot path.  The only exchange is one all-gather of the final,
+fixed-size detections buffer (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+One process per GPU (torchrun); rank r owns the contiguous image block `shard_range(...)`.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialises torch.distributed from RANK / WORLD_SIZE / MASTER_* when WORLD_SIZE > 1.
+    Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block [start, stop) of `n_items` owned by `rank`; blocks differ by at most one."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def pack_detections(boxes, probs, cls, count):
+    """(B,M,4) i32, (B,M) f32, (B,M) i32, (B,) i32 -> dets (B,M,6) f32 rows
+    [x1,y1,x2,y2,prob,class] (rows >= count zeroed) + counts (B,) i32."""
+    m = boxes.shape[1]
+    live = (torch.arange(m, device=boxes.device)[None, :] < count[:, None]).unsqueeze(-1)
+    dets = torch.cat([boxes.to(torch.float32), probs.unsqueeze(-1), cls.to(torch.float32).unsqueeze(-1)], dim=-1)
+    return torch.where(live, dets, torch.zeros((), dtype=dets.dtype, device=dets.device)), count.to(torch.int32)
+
+
+def all_gather_detections(dets, counts, group=None):
+    """Every rank contributes dets (b,M,6) f32 + counts (b,) i32 with the SAME b and M; returns the
+    image-major concatenation over ranks ((world*b, M, 6), (world*b,)).  Single-process: identity."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dets, counts
+    world = dist.get_world_size(group)
+    out_d = torch.empty((world * dets.shape[0],) + tuple(dets.shape[1:]), dtype=dets.dtype, device=dets.device)
+    out_c = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
+    dist.all_gather_into_tensor(out_d, dets.contiguous(), group=group)
+    dist.all_gather_into_tensor(out_c, counts.contiguous(), group=group)
+    return out_d, out_c

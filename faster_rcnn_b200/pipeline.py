@@ -1,0 +1,91 @@
+"""Device-resident orchestration of the inference hot path for a batch of images:
+
+    RPN head outputs (cls, regr) + conv features
+      -> decode + sanitize + validity + top-k          (K-a, proposals.cu)
+      -> greedy NMS 0.7 -> max_boxes                   (K-b, nms.cu)
+      -> the reference's 64-RoI batching/padding rule  (pad_rois, boxes.cu)
+      -> RoI layer (crop + bilinear resize, or max)    (K-d, roi.cu)
+
+which replaces `DetTrainingManager.get_det_inputs` + the RoI-layer half of `detector.predict` in
+`voc_dets.get_dets` (det_util.py:136-158, voc_dets.py:37-49, custom_layers.py:35-56) without the
+reference's per-image GPU->host->GPU round trips.  Inputs may be host numpy arrays (staged through
+pinned memory, the drop-in case) or CUDA tensors (stay on the device).  Images are independent:
+the batch dimension maps to grid.y / one CTA per image.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .runtime import get_context
+from .shared_constants import DEFAULT_ANCHORS
+
+
+class ProposalRoiPipeline:
+    def __init__(self, anchor_dims=DEFAULT_ANCHORS, stride=16, pre_nms_topk=8000, nms_thresh=0.7, max_boxes=300,
+                 num_rois=64, pool_size=7, mode="resize", device=None):
+        self.anchor_dims = np.asarray(anchor_dims)
+        self.stride, self.k, self.thresh, self.max_boxes = stride, pre_nms_topk, nms_thresh, max_boxes
+        self.num_rois, self.pool_size, self.mode = num_rois, pool_size, mode
+        self.ctx = get_context(device)
+        self._dev = {}
+        self._host = {}
+
+    # -- staging ----------------------------------------------------------------------------------
+    def _stage_in(self, name, x):
+        """host array -> persistent device buffer (async copy from pinned memory); device tensors pass."""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return x
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if not isinstance(x, torch.Tensor) else x
+        buf = self._dev.get(name)
+        if buf is None or buf.shape != t.shape:
+            buf = self._dev[name] = torch.empty(t.shape, dtype=torch.float32, device=self.ctx.device)
+        if not t.is_pinned():
+            pin = self._host.get(name)
+            if pin is None or pin.shape != t.shape:
+                pin = self._host[name] = torch.empty(t.shape, dtype=torch.float32).pin_memory()
+            pin.copy_(t)
+            t = pin
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def _stage_out(self, name, t):
+        pin = self._host.get(name)
+        if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
+            pin = self._host[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        pin.copy_(t, non_blocking=True)
+        return pin
+
+    # -- the call a user makes ----------------------------------------------------------------------
+    def run_device(self, cls, regr, feat):
+        """CUDA tensors in, CUDA tensors out; nothing synchronises.
+        cls (B,R,C,A), regr (B,R,C,4A), feat (B,R,C,Cf) ->
+        rois (B,max_boxes,4) i16, scores (B,max_boxes) f32, count (B,) i32,
+        padded_rois (B,M,4) i16, pooled (B,M,P,P,Cf) f32 [, argmax in max mode]."""
+        rois, scores, count = ops.proposals(regr, cls, self.anchor_dims, self.stride, self.k, self.thresh,
+                                            self.max_boxes)
+        padded, _ = ops.pad_rois(rois, count, self.num_rois)
+        pooled = ops.roi_forward(feat, padded, self.pool_size, self.mode)
+        return rois, scores, count, padded, pooled
+
+    def __call__(self, cls, regr, feat, on_device=None):
+        """Host (or device) arrays in; returns (rois, scores, count) as numpy on the host -- what
+        `get_det_inputs` hands back in the reference -- plus the pooled features as a CUDA tensor,
+        which stay on the device for the detector head exactly like the RoI layer's output inside the
+        reference's TF graph.  `on_device(rois, scores, count)` (optional) is invoked with the device
+        tensors before the read-back, e.g. to enqueue the multi-GPU all-gather of the final RoIs.
+        One stream synchronisation at the end."""
+        cls_d, regr_d, feat_d = self._stage_in("cls", cls), self._stage_in("regr", regr), self._stage_in("feat", feat)
+        rois, scores, count, padded, pooled = self.run_device(cls_d, regr_d, feat_d)
+        if on_device is not None:
+            on_device(rois, scores, count)
+        h_rois, h_scores, h_count = (self._stage_out("rois", rois), self._stage_out("scores", scores),
+                                     self._stage_out("count", count))
+        torch.cuda.current_stream(self.ctx.device).synchronize()
+        return h_rois.numpy(), h_scores.numpy(), h_count.numpy(), pooled
+
+    @staticmethod
+    def h2d_bytes(cls, regr, feat):
+        return 4 * (int(np.prod(cls.shape)) + int(np.prod(regr.shape)) + int(np.prod(feat.shape)))
+
+    def d2h_bytes(self, batch):
+        return batch * (self.max_boxes * 8 + self.max_boxes * 4 + 4)

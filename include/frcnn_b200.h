@@ -1,0 +1,233 @@
+/*
+ * frcnn_b200 -- C ABI of the B200-native region-proposal / target-assignment /
+ * NMS / RoI-layer hot path.
+ *
+ * The reference (Kelicious/faster_rcnn) is pure Python + numpy and has no FFI
+ * layer of its own; its boundary is the Python functions listed below.  Each
+ * entry point names the reference code it replaces (file:line under
+ * /root/reference/faster_rcnn).  The Python package `faster_rcnn_b200` binds
+ * these symbols with ctypes and re-exposes the reference's signatures
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - every function returns FRCNN_OK (0) or a negative frcnn_status; nothing
+ *    throws or aborts.  frcnn_last_error(h) gives a message for the last failure
+ *    on that handle.
+ *  - all data pointers are DEVICE pointers unless the parameter name ends in
+ *    `_host`.  The caller owns every buffer.  Work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*) and is asynchronous.
+ *  - one handle per (host thread, device); handles are not thread-safe.  A
+ *    handle owns a scratch arena that grows on demand (growing synchronises the
+ *    stream; call frcnn_reserve() up front to avoid that, e.g. before CUDA-graph
+ *    capture).
+ *  - boxes are [x1, y1, x2, y2]; a "batch" is a set of independent images laid
+ *    out contiguously (image-major).  Flat anchor index = (y*C + x)*A + a.
+ *  - arithmetic follows the reference bit for bit where it is integer / IEEE
+ *    (+1 area convention and f64 ratio in NMS, f32 no-FMA IoU in labelling);
+ *    see DESIGN.md for the two documented transcendental exceptions (expf/log).
+ */
+#ifndef FRCNN_B200_H
+#define FRCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FRCNN_API __attribute__((visibility("default")))
+#else
+#define FRCNN_API
+#endif
+
+#define FRCNN_ABI_VERSION 1
+#define FRCNN_MAX_ANCHORS 64       /* anchors per location */
+#define FRCNN_MAX_GT 256           /* GT boxes per image   */
+#define FRCNN_NMS_MAX_SORTED 22528 /* nms_i16: max n when scores arrive strictly descending */
+#define FRCNN_NMS_MAX_UNSORTED 16384 /* nms_i16: max n when the kernel has to sort        */
+#define FRCNN_NMS_F64_MAX 4096     /* nms_f64: max boxes per segment */
+
+typedef enum {
+  FRCNN_OK = 0,
+  FRCNN_ERR_INVALID = -1,     /* bad argument */
+  FRCNN_ERR_CUDA = -2,        /* CUDA runtime error (message in frcnn_last_error) */
+  FRCNN_ERR_UNSUPPORTED = -3, /* size beyond what the kernels support */
+  FRCNN_ERR_NOMEM = -4
+} frcnn_status;
+
+typedef enum { FRCNN_ROI_RESIZE = 0, FRCNN_ROI_MAX = 1 } frcnn_roi_mode;
+typedef enum { FRCNN_ROI_I16 = 0, FRCNN_ROI_I32 = 1, FRCNN_ROI_F32 = 2 } frcnn_roi_dtype;
+
+typedef struct frcnn_handle frcnn_handle;
+
+/* ---- lifetime ---------------------------------------------------------- */
+FRCNN_API int frcnn_abi_version(void);
+FRCNN_API int frcnn_create(frcnn_handle** out, int device);
+FRCNN_API void frcnn_destroy(frcnn_handle* h);
+FRCNN_API const char* frcnn_last_error(frcnn_handle* h);
+/* Pre-size the scratch arena (bytes). */
+FRCNN_API int frcnn_reserve(frcnn_handle* h, size_t bytes);
+/* Number of kernels this handle has launched so far (for bench accounting). */
+FRCNN_API long long frcnn_launch_count(frcnn_handle* h);
+
+/* ---- K-a: proposals = anchors + delta decode + sanitize + validity + top-k
+ * Replaces det_util._get_rois (det_util.py:370-380), _get_anchor_coords
+ * (:162-175), util.transform_np_inplace (util.py:111-142),
+ * _sanitize_boxes_inplace (det_util.py:179-192), _get_valid_box_idxs
+ * (:196-205) and the sort/truncate/int16 cast of det_util.py:68-76 / :147-155.
+ *   regr  [batch,R,C,4A] f32   cls [batch,R,C,A] f32
+ *   anchor_hw_host [A][2] int32 pixel [height,width] (util.get_anchors); the
+ *   library applies `// stride` itself.
+ *   out_boxes [batch,k,4] i16, out_scores [batch,k] f32, out_index [batch,k]
+ *   i32 (flat anchor index), out_count [batch] i32.  Order: score descending,
+ *   ties by descending anchor index; rows >= count are zero / index -1.
+ *   dense_boxes (optional, may be NULL) [batch,R*C*A,4] f32 receives every
+ *   decoded+sanitized box (the return value of _get_rois). */
+FRCNN_API int frcnn_decode_topk(frcnn_handle* h, void* stream, const float* regr, const float* cls,
+                      const int32_t* anchor_hw_host, int rows, int cols, int n_anchors,
+                      int stride, int k, int batch, int16_t* out_boxes, float* out_scores,
+                      int32_t* out_index, int32_t* out_count, float* dense_boxes);
+
+/* ---- K-b: greedy NMS, int16 boxes (RPN stage)
+ * Replaces det_util.nms (det_util.py:209-256) for int16 boxes.
+ *   boxes [batch,n_max,4] i16, scores [batch,n_max] f32, n [batch] i32 (device;
+ *   NULL = n_max for every image).  Visit order = (score desc, position desc),
+ *   predicate = f64(inter/union) <= thresh keeps, +1 areas, stop at max_boxes.
+ *   keep_index [batch,max_boxes] i32 positions into the image's rows (pick
+ *   order, -1 padded), keep_count [batch]; keep_boxes [batch,max_boxes,4] i16
+ *   and keep_scores [batch,max_boxes] f32 are optional (NULL to skip). */
+FRCNN_API int frcnn_nms_i16(frcnn_handle* h, void* stream, const int16_t* boxes, const float* scores,
+                  const int32_t* n, int n_max, int batch, double thresh, int max_boxes,
+                  int32_t* keep_index, int32_t* keep_count, int16_t* keep_boxes,
+                  float* keep_scores);
+
+/* ---- K-b': greedy NMS, float64 boxes, segmented (per-class stage)
+ * Replaces det_util.nms as called from voc_dets.py:76 (all-f64 arithmetic).
+ *   boxes [total,4] f64, scores [total] f32, seg_offsets [n_seg+1] i32
+ *   (device).  keep_index [n_seg,out_stride] i32 relative to the segment
+ *   start, keep_count [n_seg]. */
+FRCNN_API int frcnn_nms_f64(frcnn_handle* h, void* stream, const double* boxes, const float* scores,
+                  const int32_t* seg_offsets, int n_seg, int max_seg_len, double thresh,
+                  int max_boxes, int out_stride, int32_t* keep_index, int32_t* keep_count);
+
+/* ---- fused proposal stage: K-a feeding K-b without leaving the device.
+ * Replaces DetTrainingManager.get_det_inputs / _process up to nms
+ * (det_util.py:63-77, :136-158).  out_rois [batch,max_boxes,4] i16,
+ * out_scores [batch,max_boxes] f32, out_count [batch] i32. */
+FRCNN_API int frcnn_proposals(frcnn_handle* h, void* stream, const float* regr, const float* cls,
+                    const int32_t* anchor_hw_host, int rows, int cols, int n_anchors, int stride,
+                    int k, double thresh, int max_boxes, int batch, int16_t* out_rois,
+                    float* out_scores, int32_t* out_count);
+
+/* ---- K-c: RPN anchor labelling
+ * Replaces RpnTrainingManager._process (rpn_util.py:54-103) incl.
+ * _get_all_anchor_coords (:276-298), _get_out_of_bounds_idxs (:302-310),
+ * util.cross_ious (util.py:146-177) and util.get_reg_params (:180-206).
+ *   gt [batch,g_max,4] f32 pixel corners, n_gt [batch] i32, img_wh [batch,2]
+ *   i32 (width,height).  can_use/is_pos [batch,N] u8, bbreg [batch,N,4] f32,
+ *   counts [batch,2] i32 = (#pos&can_use, #neg&can_use) before sampling. */
+FRCNN_API int frcnn_label_anchors(frcnn_handle* h, void* stream, const float* gt, const int32_t* n_gt,
+                        const int32_t* img_wh, int g_max, int rows, int cols, int n_anchors,
+                        const int32_t* anchor_hw_host, int stride, int batch, uint8_t* can_use,
+                        uint8_t* is_pos, float* bbreg, int32_t* counts);
+
+/* ---- T6/T7: apply host-drawn sampling and pack Keras y_true tensors
+ * Replaces _apply_sampling (rpn_util.py:324-350) and the tail of
+ * RpnTrainingManager.rpn_y_true (rpn_util.py:124-140).
+ *   off_pos / off_neg (device, may be NULL): the values the reference draws with
+ *   random.sample(range(num_pos), ..) / random.sample(range(num_neg), ..), i.e. RANKS
+ *   among the image's usable positives / negatives in ascending anchor order (counts
+ *   come from frcnn_label_anchors); off_*_offsets [batch+1] i32 delimit each image's
+ *   slice.  The anchors at those ranks get can_use = 0 (in place, like the reference),
+ *   then y_class [batch,R,C,2A] u8 = [can_use | is_pos] and y_bbreg [batch,R,C,8A] f32 =
+ *   [repeat(is_pos & can_use, 4) | targets] are written. */
+FRCNN_API int frcnn_pack_rpn_targets(frcnn_handle* h, void* stream, uint8_t* can_use, const uint8_t* is_pos,
+                                     const float* bbreg, const int32_t* off_pos,
+                                     const int32_t* off_pos_offsets, const int32_t* off_neg,
+                                     const int32_t* off_neg_offsets, int rows, int cols, int n_anchors,
+                                     int batch, uint8_t* y_class, float* y_bbreg);
+
+/* ---- K-c': detector RoI labelling
+ * Replaces det_util._rois_to_truth (det_util.py:310-334),
+ * _one_hot_encode_bbreg (:338-354) and _one_hot_encode_cls (:358-366).
+ *   rois [batch,n_max,4] i16, n_roi [batch] (NULL = n_max), gt [batch,g_max,4]
+ *   f64 in FEATURE units (pixel corner * (1/stride), python-float precision),
+ *   gt_cls [batch,g_max] i32, n_gt [batch], n_classes incl. 'bg' (= last).
+ *   Outputs are compacted to the eligible rows (max IoU >= 0.1), order kept:
+ *   out_rois [batch,n_max,4] i16, out_cls [batch,n_max,K] i32 one-hot,
+ *   out_bbreg [batch,n_max,8(K-1)] f32, out_src [batch,n_max] i32 (row of the
+ *   input RoI, optional), out_count [batch]. */
+FRCNN_API int frcnn_label_rois(frcnn_handle* h, void* stream, const int16_t* rois, const int32_t* n_roi,
+                     int n_max, const double* gt, const int32_t* gt_cls, const int32_t* n_gt,
+                     int g_max, int n_classes, int batch, int16_t* out_rois, int32_t* out_cls,
+                     float* out_bbreg, int32_t* out_src, int32_t* out_count);
+
+/* ---- K-d: RoI layer forward / backward
+ * Replaces custom_layers.RoiResizeConv.call (custom_layers.py:35-56) and its
+ * TF autodiff gradient.  mode RESIZE = crop + TF-1.3 legacy bilinear resize
+ * (reference behaviour); mode MAX = max pooling (north-star addition).
+ *   feat [batch,H,W,C] f32 channels-last, rois [batch,N,4] (dtype per
+ *   roi_dtype, truncated to int like K.cast(...,'int32'); x2/y2 exclusive),
+ *   out [batch,N,P,P,C] f32, argmax [batch,N,P,P,C] i32 (MAX mode only).
+ *   Backward: grad_out like out; grad_feat [batch,H,W,C] f32 is overwritten. */
+FRCNN_API int frcnn_roi_fwd(frcnn_handle* h, void* stream, int mode, const float* feat, int height,
+                  int width, int channels, const void* rois, int roi_dtype, int n_rois, int pool,
+                  int batch, float* out, int32_t* argmax);
+FRCNN_API int frcnn_roi_bwd(frcnn_handle* h, void* stream, int mode, const float* grad_out,
+                  const void* rois, int roi_dtype, const int32_t* argmax, int height, int width,
+                  int channels, int n_rois, int pool, int batch, float* grad_feat);
+
+/* ---- K-e: detector post-processing
+ * Replaces the loops of voc_dets.get_dets (voc_dets.py:51-86): per-row argmax
+ * class, f64 decode (util.transform, util.py:55-74), x stride, per-class f64
+ * NMS, rescale + half-even rounding.
+ *   rois [batch,M,4] i16, out_cls [batch,M,K] f32, out_reg [batch,M,4(K-1)]
+ *   f32, resize_ratio [batch] f64.  det_boxes [batch,M,4] i32, det_probs
+ *   [batch,M] f32, det_cls [batch,M] i32, det_count [batch]; order = classes by
+ *   first appearance, rows in NMS pick order. */
+FRCNN_API int frcnn_det_postprocess(frcnn_handle* h, void* stream, const int16_t* rois, const float* out_cls,
+                          const float* out_reg, const double* resize_ratio, int m_rows,
+                          int n_classes, int bg_index, int stride, double det_threshold,
+                          double nms_thresh, int max_boxes, int batch, int32_t* det_boxes,
+                          float* det_probs, int32_t* det_cls, int32_t* det_count);
+
+/* ---- stand-alone helpers behind the reference's module-level functions ------------------ */
+
+/* util.cross_ious (util.py:146-177): iou [n, n_gt] f32, no +1 convention, float32 op order of
+ * the reference.  boxes [n,4] int16 (box_dtype FRCNN_ROI_I16; areas wrap in int16 like numpy's)
+ * or float32 (FRCNN_ROI_F32); gt [n_gt,4] f32. */
+FRCNN_API int frcnn_cross_ious(frcnn_handle* h, void* stream, const void* boxes, int box_dtype, int n,
+                     const float* gt, int n_gt, float* iou);
+
+/* util.transform_np_inplace (util.py:111-142) when decode != 0, then
+ * det_util._sanitize_boxes_inplace (det_util.py:179-192) when sanitize_cols/rows > 0.
+ * boxes [n,4] f32 are updated in place; deltas [n,4] f32 = (tx,ty,tw,th) already divided by
+ * BBREG_MULTIPLIERS. */
+FRCNN_API int frcnn_box_transform(frcnn_handle* h, void* stream, float* boxes, const float* deltas, int n,
+                        int decode, int sanitize_cols, int sanitize_rows);
+
+/* Anchor boxes [rows,cols,A,4] f32.  pixel_space == 0: det_util._get_anchor_coords
+ * (det_util.py:162-175), centre = cell index, `stride` ignored, dims used as given.
+ * pixel_space != 0: rpn_util._get_all_anchor_coords (rpn_util.py:276-298), centre =
+ * int(stride * (cell + 0.5)). */
+FRCNN_API int frcnn_anchor_grid(frcnn_handle* h, void* stream, const int32_t* anchor_hw_host, int n_anchors,
+                      int rows, int cols, int stride, int pixel_space, float* out);
+
+/* det_util._get_valid_box_idxs (det_util.py:196-205): ascending indices of boxes [n,4] f32
+ * with x2 > x1 and y2 > y1; out_index [n] i32, out_count [1] i32. */
+FRCNN_API int frcnn_valid_boxes(frcnn_handle* h, void* stream, const float* boxes, int n, int32_t* out_index,
+                      int32_t* out_count);
+
+/* RoI batching rule of voc_dets.get_dets (voc_dets.py:37-46): the detector takes `group` RoIs at
+ * a time and the last batch is padded with copies of its first RoI.  rois [batch,n_max,4] i16,
+ * count [batch] -> out [batch,m_out,4] i16 with m_out >= n_max rounded up to `group`; rows past
+ * the padded length are the empty box [0,0,0,0]; out_rows [batch] = count rounded up. */
+FRCNN_API int frcnn_pad_rois(frcnn_handle* h, void* stream, const int16_t* rois, const int32_t* count,
+                             int n_max, int group, int m_out, int batch, int16_t* out, int32_t* out_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRCNN_B200_H */

@@ -1,0 +1,291 @@
+"""GPU parity: proposal stage (K-a decode/top-k, K-b NMS) through the C ABI vs the numpy oracle
+and the reference-generated golden vectors.  Bit-exact for boxes/indices/keep lists.
+
+The only tolerated difference is the documented transcendental exception: CUDA `expf` and numpy's
+SIMD `exp` differ by ulps, which can flip the half-to-even rounding of a decoded coordinate by
+one cell in ~1e-5 of the anchors.  Downstream stages are therefore compared against
+the oracle run on the SAME decoded boxes, and the flip count is asserted tiny."""
+import numpy as np
+import pytest
+
+from helpers import dev, flipped_rows, golden, host
+from oracle import frcnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MAX_FLIPS = 3
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from faster_rcnn_b200 import ops as _ops
+    return _ops
+
+
+def _synth(rows, cols, scales, seed, clustered):
+    from faster_rcnn_b200 import synth
+    dims = O.anchor_table(scales) if scales else O.anchor_table()
+    cls, regr = synth.rpn_outputs(rows, cols, len(dims), seed, clustered=clustered)
+    return dims, cls, regr
+
+
+def _check_decode_topk(ops, dims, cls, regr, k, want_dense=None):
+    boxes, scores, index, count, dense = ops.decode_topk(dev(regr), dev(cls), dims, 16, k, want_dense=True)
+    dense = host(dense)[0]
+    if want_dense is None:
+        want_dense = O.proposals_from_rpn(regr.copy(), dims, 16)
+    flips = flipped_rows(dense, want_dense)
+    assert len(flips) <= MAX_FLIPS, "decode: %d rows differ from the oracle" % len(flips)
+    if len(flips):
+        assert np.abs(dense[flips] - want_dense[flips]).max() <= 1.0
+    # top-k is exact given the decoded boxes
+    wb, wp, widx = O.topk_proposals(dense.copy(), cls.reshape(-1), k)
+    n = int(host(count)[0])
+    assert n == len(wb)
+    assert np.array_equal(host(boxes)[0, :n], wb) and np.array_equal(host(scores)[0, :n], wp)
+    assert np.array_equal(host(index)[0, :n], widx)
+    assert np.all(host(index)[0, n:] == -1)
+    return dense, len(flips)
+
+
+@pytest.mark.parametrize("rows,cols,scales,seed,k,clustered", [
+    (38, 63, [128, 256, 512], 1, 8000, False),      # C1 VOC ResNet-50
+    (38, 63, [128, 256, 512], 2, 12000, True),      # training k
+    (38, 94, None, 3, 12000, True),                 # C3 KITTI, 18 anchors incl. zero-sized feature anchors
+    (38, 94, None, 4, 8000, False),
+    (37, 62, [128, 256, 512], 5, 8000, False),      # VGG16 map
+    (5, 7, [128, 256, 512], 6, 8000, False),        # k > number of anchors
+    (1, 1, [128, 256, 512], 7, 4, False),
+])
+def test_decode_topk_vs_oracle(ops, rows, cols, scales, seed, k, clustered):
+    dims, cls, regr = _synth(rows, cols, scales, seed, clustered)
+    _check_decode_topk(ops, dims, cls, regr, k)
+
+
+@pytest.mark.parametrize("tag", ["voc_small", "voc_clustered", "kitti_small"])
+def test_proposal_stage_vs_golden(ops, tag):
+    g = golden("proposals_" + tag)
+    k, max_boxes = int(g["k"]), int(g["max_boxes"])
+    dense, n_flips = _check_decode_topk(ops, g["anchor_dims"], g["cls"], g["regr"], k, want_dense=g["dense"])
+    # NMS kernel on the reference's own top-k boxes: bit-exact keep list
+    ki, kc, kb, ks = ops.nms_i16(dev(g["topk_boxes"][None]), dev(g["topk_probs"][None]), None, 0.7, max_boxes)
+    n = int(host(kc)[0])
+    assert n == len(g["nms_boxes"])
+    assert np.array_equal(host(kb)[0, :n], g["nms_boxes"]) and np.array_equal(host(ks)[0, :n], g["nms_probs"])
+    # fused decode -> top-k -> NMS on the device
+    rois, scores, count = ops.proposals(dev(g["regr"]), dev(g["cls"]), g["anchor_dims"], 16, k, 0.7, max_boxes)
+    if n_flips == 0:
+        n = int(host(count)[0])
+        assert np.array_equal(host(rois)[0, :n], g["nms_boxes"]) and np.array_equal(host(scores)[0, :n], g["nms_probs"])
+
+
+@pytest.mark.parametrize("rows,cols,scales,seed,k,max_boxes,clustered", [
+    (38, 63, [128, 256, 512], 11, 8000, 300, False),
+    (38, 63, [128, 256, 512], 12, 8000, 300, True),
+    (38, 63, [128, 256, 512], 13, 12000, 2000, True),
+    (38, 94, None, 14, 12000, 2000, True),
+    (38, 94, None, 15, 8000, 300, False),
+])
+def test_fused_proposals_vs_oracle(ops, rows, cols, scales, seed, k, max_boxes, clustered):
+    dims, cls, regr = _synth(rows, cols, scales, seed, clustered)
+    dense = host(ops.decode_topk(dev(regr), dev(cls), dims, 16, k, want_dense=True)[4])[0]
+    wb, wp, _ = O.topk_proposals(dense.copy(), cls.reshape(-1), k)
+    pick = O.greedy_nms(wb, wp, 0.7, max_boxes)
+    rois, scores, count = ops.proposals(dev(regr), dev(cls), dims, 16, k, 0.7, max_boxes)
+    n = int(host(count)[0])
+    assert n == len(pick)
+    assert np.array_equal(host(rois)[0, :n], wb[pick]) and np.array_equal(host(scores)[0, :n], wp[pick])
+    assert np.all(host(rois)[0, n:] == 0)
+
+
+def test_fused_proposals_batch(ops):
+    """A batch of images = independent problems in one launch sequence."""
+    dims = O.anchor_table([128, 256, 512])
+    from faster_rcnn_b200 import synth
+    pairs = [synth.rpn_outputs(38, 63, 9, 20 + i, clustered=bool(i % 2)) for i in range(5)]
+    cls = np.concatenate([p[0] for p in pairs])
+    regr = np.concatenate([p[1] for p in pairs])
+    rois, scores, count = ops.proposals(dev(regr), dev(cls), dims, 16, 8000, 0.7, 300)
+    for b in range(5):
+        one_r, one_s, one_c = ops.proposals(dev(regr[b:b + 1]), dev(cls[b:b + 1]), dims, 16, 8000, 0.7, 300)
+        n = int(host(one_c)[0])
+        assert int(host(count)[b]) == n
+        assert np.array_equal(host(rois)[b], host(one_r)[0]) and np.array_equal(host(scores)[b], host(one_s)[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# NMS kernel in isolation
+# ------------------------------------------------------------------------------------------------
+def _rand_boxes_i16(rng, n, size=64, max_wh=24):
+    x1 = rng.integers(0, size - 1, n)
+    y1 = rng.integers(0, size - 1, n)
+    x2 = np.minimum(size - 1, x1 + 1 + rng.integers(0, max_wh, n))
+    y2 = np.minimum(size - 1, y1 + 1 + rng.integers(0, max_wh, n))
+    return np.stack([x1, y1, x2, y2], axis=1).astype(np.int16)
+
+
+def _nms_dev(ops, boxes, probs, thresh, max_boxes):
+    ki, kc, kb, ks = ops.nms_i16(dev(boxes[None]), dev(probs[None]), None, thresh, max_boxes)
+    n = int(host(kc)[0])
+    assert np.all(host(ki)[0, n:] == -1)
+    return host(ki)[0, :n], host(kb)[0, :n], host(ks)[0, :n]
+
+
+@pytest.mark.parametrize("n,thresh,max_boxes", [
+    (1, 0.7, 300), (2, 0.7, 300), (63, 0.7, 300), (64, 0.7, 300), (65, 0.7, 300), (129, 0.5, 10),
+    (1000, 0.7, 300), (1001, 0.3, 2000), (4097, 0.7, 300), (8000, 0.7, 300), (12000, 0.7, 2000),
+    (16384, 0.7, 300), (500, 0.0, 300), (500, 1.0, 300), (500, 0.7, 1),
+])
+def test_nms_i16_unsorted_vs_oracle(ops, n, thresh, max_boxes):
+    rng = np.random.default_rng(n)
+    boxes = _rand_boxes_i16(rng, n)
+    probs = (rng.permutation(n).astype(np.float32) + 0.5) / n          # unique, arbitrary order
+    pick = O.greedy_nms(boxes, probs, thresh, max_boxes)
+    ki, kb, ks = _nms_dev(ops, boxes, probs, thresh, max_boxes)
+    assert np.array_equal(ki, pick) and np.array_equal(kb, boxes[pick]) and np.array_equal(ks, probs[pick])
+
+
+@pytest.mark.parametrize("n", [2, 100, 3001, 20000])
+def test_nms_i16_sorted_input_tma_path(ops, n):
+    """strictly descending scores (the layout K-a emits): identity order, bulk-copy load path;
+    odd n exercises the non-16-byte-multiple fallback; n = 20000 > FRCNN_NMS_MAX_UNSORTED."""
+    rng = np.random.default_rng(n + 7)
+    boxes = _rand_boxes_i16(rng, n, size=96)
+    probs = np.sort((rng.permutation(n).astype(np.float32) + 0.5) / n)[::-1].copy()
+    pick = O.greedy_nms(boxes, probs, 0.7, 300)
+    ki, kb, ks = _nms_dev(ops, boxes, probs, 0.7, 300)
+    assert np.array_equal(ki, pick) and np.array_equal(kb, boxes[pick])
+
+
+def test_nms_i16_ties_follow_the_stable_order(ops):
+    """equal scores: visit order = (score desc, position desc), i.e. argsort(kind='stable') from the back."""
+    rng = np.random.default_rng(3)
+    boxes = _rand_boxes_i16(rng, 2000)
+    probs = (rng.integers(0, 40, 2000) / 40).astype(np.float32)
+    pick = O.greedy_nms(boxes, probs, 0.7, 300, stable=True)
+    ki, _, _ = _nms_dev(ops, boxes, probs, 0.7, 300)
+    assert np.array_equal(ki, pick)
+    same = np.tile(np.array([[3, 4, 20, 30]], dtype=np.int16), (70, 1))           # all identical boxes
+    ki, _, _ = _nms_dev(ops, same, np.ones(70, dtype=np.float32), 0.7, 300)
+    assert ki.tolist() == [69]
+
+
+def test_nms_i16_exact_threshold_boundary(ops):
+    """inter/union == 0.7 exactly must survive (<=), one cell more must not; the reference divides in f64."""
+    a = [0, 0, 9, 9]                       # area 100
+    b = [0, 3, 9, 9]                       # area 70, inter 70, union 100 -> 0.7 exactly
+    c = [0, 2, 9, 9]                       # area 80 -> 0.8
+    boxes = np.array([a, b, c], dtype=np.int16)
+    probs = np.array([0.9, 0.8, 0.7], dtype=np.float32)
+    pick = O.greedy_nms(boxes, probs, 0.7, 300)
+    ki, _, _ = _nms_dev(ops, boxes, probs, 0.7, 300)
+    assert pick.tolist() == [0, 1] and ki.tolist() == [0, 1]
+
+
+def test_nms_i16_ragged_batch(ops):
+    rng = np.random.default_rng(9)
+    ns = [0, 1, 777, 4000, 64]
+    n_max = max(ns)
+    boxes = np.zeros((len(ns), n_max, 4), dtype=np.int16)
+    probs = np.zeros((len(ns), n_max), dtype=np.float32)
+    for b, n in enumerate(ns):
+        boxes[b, :n] = _rand_boxes_i16(rng, n)
+        probs[b, :n] = (rng.permutation(n).astype(np.float32) + 0.5) / max(n, 1)
+    ki, kc, kb, ks = ops.nms_i16(dev(boxes), dev(probs), dev(np.array(ns, dtype=np.int32)), 0.7, 300)
+    for b, n in enumerate(ns):
+        pick = O.greedy_nms(boxes[b, :n], probs[b, :n], 0.7, 300)
+        assert int(host(kc)[b]) == len(pick)
+        assert np.array_equal(host(ki)[b, :len(pick)], pick)
+
+
+def test_nms_properties_full_size(ops):
+    """size-independent properties at BASELINE's full size (12000 -> 2000): kept boxes are pairwise
+    below the threshold, every dropped box ahead of the cut is covered by an earlier kept one, and
+    NMS of the kept set is the identity (idempotence)."""
+    from faster_rcnn_b200 import synth
+    dims = O.anchor_table()
+    cls, regr = synth.rpn_outputs(38, 94, 18, 77, clustered=True)
+    tb, ts, _, tc = ops.decode_topk(dev(regr), dev(cls), dims, 16, 12000)
+    n = int(host(tc)[0])
+    ki, kc, kb, ks = ops.nms_i16(tb, ts, tc, 0.7, 2000)
+    m = int(host(kc)[0])
+    boxes, keep = host(tb)[0, :n].astype(np.int64), host(ki)[0, :m]
+    assert np.all(np.diff(keep) > 0)                       # pick order = descending score = ascending position
+    area = (boxes[:, 2] - boxes[:, 0] + 1) * (boxes[:, 3] - boxes[:, 1] + 1)
+
+    def over(i_idx, j_idx):                                 # exact integer test of inter/union > 0.7
+        a, b = boxes[i_idx][:, None, :], boxes[j_idx][None, :, :]
+        iw = np.maximum(0, np.minimum(a[..., 2], b[..., 2]) - np.maximum(a[..., 0], b[..., 0]) + 1)
+        ih = np.maximum(0, np.minimum(a[..., 3], b[..., 3]) - np.maximum(a[..., 1], b[..., 1]) + 1)
+        inter = iw * ih
+        union = area[i_idx][:, None] + area[j_idx][None, :] - inter
+        return 10 * inter > 7 * union
+    kk = over(keep, keep)
+    np.fill_diagonal(kk, False)
+    assert not kk.any()
+    last = keep[-1]
+    dropped = np.setdiff1d(np.arange(last), keep)
+    cover = over(dropped, keep) & (keep[None, :] < dropped[:, None])
+    assert cover.any(axis=1).all()
+    ki2, kc2, _, _ = ops.nms_i16(kb[:, :m].contiguous(), ks[:, :m].contiguous(), None, 0.7, 2000)
+    assert int(host(kc2)[0]) == m and np.array_equal(host(ki2)[0, :m], np.arange(m))
+
+
+# ------------------------------------------------------------------------------------------------
+# float64 segmented NMS
+# ------------------------------------------------------------------------------------------------
+def test_nms_f64_vs_golden_and_oracle(ops):
+    g = golden("nms_f64_iou")
+    offs = dev(np.array([0, 400], dtype=np.int32))
+    ki, kc = ops.nms_f64(dev(g["boxes"]), dev(g["probs"]), offs, 400, 0.5, 2000)
+    n = int(host(kc)[0])
+    pick = host(ki)[0, :n]
+    assert np.array_equal(g["boxes"][pick], g["nms_boxes"]) and np.array_equal(g["probs"][pick], g["nms_probs"])
+    # several segments of different length incl. an empty one, ties inside a segment
+    rng = np.random.default_rng(21)
+    lens = [0, 1, 37, 320, 5]
+    total = sum(lens)
+    xy, wh = rng.uniform(0, 300, (total, 2)), rng.uniform(5, 150, (total, 2))
+    boxes = np.concatenate([xy, xy + wh], axis=1)
+    probs = (rng.integers(0, 50, total) / 50).astype(np.float32)
+    so = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ki, kc = ops.nms_f64(dev(boxes), dev(probs), dev(so), max(lens), 0.5, 2000)
+    for s, ln in enumerate(lens):
+        pick = O.greedy_nms(boxes[so[s]:so[s + 1]], probs[so[s]:so[s + 1]], 0.5, 2000)
+        assert int(host(kc)[s]) == len(pick) and np.array_equal(host(ki)[s, :len(pick)], pick)
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in module surface (numpy in / numpy out)
+# ------------------------------------------------------------------------------------------------
+def test_dropin_det_util_functions():
+    from faster_rcnn_b200 import det_util, synth
+    g = golden("proposals_voc_clustered")
+    rois = det_util._get_rois(g["regr"], g["anchor_dims"], 16)
+    flips = flipped_rows(rois, g["dense"])
+    assert rois.dtype == np.float32 and len(flips) <= MAX_FLIPS
+    assert np.array_equal(det_util._get_valid_box_idxs(g["dense"]), g["valid"])
+    nb, npb = det_util.nms(g["topk_boxes"], g["topk_probs"], max_boxes=int(g["max_boxes"]), overlap_thresh=0.7)
+    assert nb.dtype == np.int16 and np.array_equal(nb, g["nms_boxes"]) and np.array_equal(npb, g["nms_probs"])
+    assert det_util.nms(g["topk_boxes"][:0], g["topk_probs"][:0]) == []
+    f = golden("nms_f64_iou")
+    nb, npb = det_util.nms(f["boxes"], f["probs"], overlap_thresh=0.5, max_boxes=2000)
+    assert nb.dtype == np.float64 and np.array_equal(nb, f["nms_boxes"]) and np.array_equal(npb, f["nms_probs"])
+    # anchors + sanitize helpers
+    dims = O.anchor_table() // 16
+    anc = det_util._get_anchor_coords(7, 9, dims)
+    assert anc.shape == (7, 9, 18, 4) and np.array_equal(anc.reshape(-1, 4), O.feature_anchors(7, 9, dims))
+    rng = np.random.default_rng(1)
+    raw = np.round(rng.normal(20, 30, (500, 4))).astype(np.float32)
+    want = O.sanitize_boxes(63, 38, raw.copy())
+    got = det_util._sanitize_boxes_inplace(63, 38, raw)
+    assert got is raw and np.array_equal(raw, want)
+    cls, regr = synth.rpn_outputs(38, 63, 9, 31)
+    from helpers import FakeImage, FakeRpn
+    mgr = det_util.DetTrainingManager(FakeRpn(cls, regr, conv=np.zeros((1, 38, 63, 8), np.float32)),
+                                      synth.VOC_CLASS_MAPPING, lambda d: d, anchor_dims=O.anchor_table([128, 256, 512]))
+    conv, rois = mgr.get_det_inputs(FakeImage("a", 1000, 600, [], data=np.zeros((600, 1000, 3), np.float32)))
+    dense = det_util._get_rois(regr, O.anchor_table([128, 256, 512]), 16)
+    wb, wp, _ = O.topk_proposals(dense.copy(), cls.reshape(-1), 8000)
+    pick = O.greedy_nms(wb, wp, 0.7, 300)
+    assert mgr.conv_only and conv.shape == (1, 38, 63, 8) and rois.dtype == np.int16 and np.array_equal(rois, wb[pick])

@@ -1,0 +1,63 @@
+"""Cross-checks the RoI-layer oracle (parity unpinned: TensorFlow 1.3 is unavailable) against an independent
+formulation: torch.nn.functional.grid_sample on explicit legacy-coordinate grids (tolerance only), and checks
+its backward against torch autograd of that formulation.  CPU only."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import roi_oracle as R
+
+
+def _torch_resize(feat, rois, pool):
+    """crop + legacy bilinear (src = i * in/out, clamp at the border) via grid_sample(align_corners=True)."""
+    outs = []
+    for x1, y1, x2, y2 in rois.tolist():
+        crop = feat[y1:y2, x1:x2].permute(2, 0, 1)[None]                     # (1,C,h,w)
+        h, w = crop.shape[2:]
+        sy = torch.arange(pool, dtype=torch.float64) * (h / pool)
+        sx = torch.arange(pool, dtype=torch.float64) * (w / pool)
+        gy = (2 * sy / (h - 1) - 1) if h > 1 else torch.zeros(pool, dtype=torch.float64)
+        gx = (2 * sx / (w - 1) - 1) if w > 1 else torch.zeros(pool, dtype=torch.float64)
+        grid = torch.stack(torch.meshgrid(gy, gx, indexing='ij')[::-1], dim=-1)[None]
+        outs.append(F.grid_sample(crop.double(), grid, mode='bilinear', padding_mode='border', align_corners=True)[0]
+                    .permute(1, 2, 0))
+    return torch.stack(outs)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_resize_forward_and_backward_match_grid_sample(seed):
+    rng = np.random.default_rng(seed)
+    h, w, c, n = 13, 16, 5, 12
+    feat = rng.standard_normal((h, w, c)).astype(np.float32)
+    x1, y1 = rng.integers(0, w - 1, n), rng.integers(0, h - 1, n)
+    rois = np.stack([x1, y1, np.minimum(w, x1 + 1 + rng.integers(0, w, n)), np.minimum(h, y1 + 1 + rng.integers(0, h, n))], 1)
+    got = R.roi_resize_fwd(feat, rois, 7)
+    ft = torch.from_numpy(feat).double().requires_grad_(True)
+    want = _torch_resize(ft, torch.from_numpy(rois), 7)
+    assert np.abs(got - want.detach().numpy()).max() < 1e-5
+    gout = rng.standard_normal(got.shape).astype(np.float32)
+    (want * torch.from_numpy(gout).double()).sum().backward()
+    assert np.abs(R.roi_resize_bwd(gout, rois, feat.shape) - ft.grad.numpy()).max() < 1e-4
+
+
+def test_resize_identity_and_upsample():
+    feat = np.arange(7 * 7 * 2, dtype=np.float32).reshape(7, 7, 2)
+    assert np.array_equal(R.roi_resize_fwd(feat, np.array([[0, 0, 7, 7]]), 7)[0], feat)
+    one = R.roi_resize_fwd(feat, np.array([[3, 2, 4, 3]]), 7)[0]             # 1x1 crop -> constant
+    assert np.array_equal(one, np.broadcast_to(feat[2, 3], (7, 7, 2)))
+
+
+def test_max_pool_spec():
+    rng = np.random.default_rng(3)
+    feat = rng.standard_normal((9, 11, 4)).astype(np.float32)
+    rois = np.array([[0, 0, 11, 9], [2, 1, 5, 3], [4, 4, 5, 5], [1, 0, 10, 8]])
+    out, arg = R.roi_max_fwd(feat, rois, 7)
+    flat = feat.reshape(-1, 4)
+    assert np.array_equal(np.take_along_axis(flat, arg.reshape(-1, 4), 0).reshape(out.shape), out)
+    # every cell of the crop belongs to at least one bin: the global max of the crop is an output
+    for r, (x1, y1, x2, y2) in enumerate(rois):
+        assert np.array_equal(out[r].max(axis=(0, 1)), feat[y1:y2, x1:x2].max(axis=(0, 1)))
+    gout = rng.standard_normal(out.shape).astype(np.float32)
+    dx = R.roi_max_bwd(gout, arg, feat.shape)
+    assert abs(float(dx.sum()) - float(gout.sum())) < 1e-3
