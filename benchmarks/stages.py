@@ -1,0 +1,152 @@
+#!/usr/bin/env python
+"""Per-stage device timings at the BASELINE.json configs (C1..C5) with CUDA events.
+
+    python benchmarks/stages.py [--iters 20] [--only roi_fwd,nms] [--json gpurun_out/stages.json]
+
+Every stage is timed alone on device-resident inputs (warm-up, then the mean of `iters` launches bracketed by
+events on the launching stream); HBM-bound stages also report algorithmic GB/s against the measured copy peak.
+Inputs are larger than L2 where the stage's working set allows it; the small latency-bound stages (NMS, top-k,
+labelling) are L2-resident by nature and are reported as latency per image.  This script is the source of the
+per-kernel tables in DESIGN.md / profiles/ and the target of the ncu captures; bench.py is the contract line."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from faster_rcnn_b200 import ops, synth          # noqa: E402
+from faster_rcnn_b200.util import get_anchors    # noqa: E402
+
+PEAK = 6551.0
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def dev(x, dtype=None):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=dtype)).cuda()
+
+
+def timeit(fn, iters, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def rpn_batch(rows, cols, dims, batch, seed, clustered):
+    pairs = [synth.rpn_outputs(rows, cols, len(dims), seed + i, clustered=clustered) for i in range(batch)]
+    return dev(np.concatenate([p[0] for p in pairs])), dev(np.concatenate([p[1] for p in pairs]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    want = lambda name: not only or any(name.startswith(o) for o in only)   # noqa: E731
+    res = []
+
+    def rec(name, config, ms, images=1, algo_bytes=None, **extra):
+        row = {"stage": name, "config": config, "ms": round(ms, 5), "images": images, "ms_per_image": round(ms / images, 5)}
+        if algo_bytes is not None:
+            row.update(algo_MB=round(algo_bytes / 1e6, 2), GBps=round(algo_bytes / ms / 1e6, 1),
+                       frac_of_measured_peak=round(algo_bytes / ms / 1e6 / PEAK, 4))
+        row.update(extra)
+        res.append(row)
+        print(json.dumps(row), flush=True)
+
+    voc, kitti = get_anchors([128, 256, 512]), get_anchors()
+    # ---- proposal stage: C1 (VOC test), C3 (KITTI train), batch 1 (latency) and batch 64 (throughput) ------------
+    for tag, rows, cols, dims, k, post, clustered in (("C1 voc 8000->300", 38, 63, voc, 8000, 300, False),
+                                                      ("C1 voc clustered 8000->300", 38, 63, voc, 8000, 300, True),
+                                                      ("C1 voc train 12000->2000 clustered", 38, 63, voc, 12000, 2000, True),
+                                                      ("C3 kitti 12000->2000 clustered", 38, 94, kitti, 12000, 2000, True),
+                                                      ("C3 kitti 8000->300", 38, 94, kitti, 8000, 300, False)):
+        for batch in (1, 64):
+            if not (want("decode") or want("nms") or want("proposals")):
+                continue
+            cls, regr = rpn_batch(rows, cols, dims, batch, 100, clustered)
+            n = rows * cols * len(dims)
+            if want("decode"):
+                ms = timeit(lambda: ops.decode_topk(regr, cls, dims, 16, k), args.iters)
+                rec("decode_topk", "%s b%d" % (tag, batch), ms, batch, batch * (n * 20 + min(k, n) * 16))
+            tb, ts, _, tc = ops.decode_topk(regr, cls, dims, 16, k)
+            if want("nms"):
+                ms = timeit(lambda: ops.nms_i16(tb, ts, tc, 0.7, post), args.iters)
+                kept = int(ops.nms_i16(tb, ts, tc, 0.7, post)[1].float().mean().item())
+                rec("nms_i16", "%s b%d" % (tag, batch), ms, batch, kept_mean=kept)
+            if want("proposals"):
+                ms = timeit(lambda: ops.proposals(regr, cls, dims, 16, k, 0.7, post), args.iters)
+                rec("proposals_fused", "%s b%d" % (tag, batch), ms, batch)
+
+    # ---- RoI layer: C1 (320 RoIs) x 64 images, C5 (2000 RoIs, 1 image and 8 images), forward + backward, both modes --
+    for tag, n_rois, batch in (("C1 320 rois", 320, 64), ("C5 2000 rois", 2000, 1), ("C5 2000 rois", 2000, 8)):
+        if not (want("roi_fwd") or want("roi_bwd")):
+            continue
+        h, w, c, p = 38, 63, 1024, 7
+        feat = torch.randn((batch, h, w, c), device="cuda")
+        rois = dev(np.stack([synth.random_rois(n_rois, h, w, 7 + i) for i in range(batch)]))
+        out_b = 4 * batch * n_rois * p * p * c
+        in_b = 4 * batch * h * w * c + 8 * batch * n_rois
+        for mode in ("resize", "max"):
+            if want("roi_fwd"):
+                ms = timeit(lambda: ops.roi_forward(feat, rois, p, mode), args.iters)
+                rec("roi_fwd_" + mode, "%s b%d" % (tag, batch), ms, batch, in_b + out_b * (2 if mode == "max" else 1))
+            if want("roi_bwd"):
+                gout = torch.randn((batch, n_rois, p, p, c), device="cuda")
+                arg = ops.roi_forward(feat, rois, p, "max")[1] if mode == "max" else None
+                ms = timeit(lambda: ops.roi_backward(gout, rois, (batch, h, w, c), mode, arg), max(3, args.iters // 4), 2)
+                rec("roi_bwd_" + mode, "%s b%d" % (tag, batch), ms, batch, in_b + out_b * (2 if mode == "max" else 1))
+                del gout, arg
+        del feat
+
+    # ---- C4 training targets: batch 128, 50 GT ---------------------------------------------------------------------
+    if want("label"):
+        batch, rows, cols = 128, 38, 63
+        gts = np.stack([np.array([g[1:] for g in synth.gt_boxes(50, 1000, 600, 300 + i)], np.float32) for i in range(batch)])
+        gt, n_gt = dev(gts), dev(np.full(batch, 50, np.int32))
+        wh = dev(np.tile(np.array([[1000, 600]], np.int32), (batch, 1)))
+        ms = timeit(lambda: ops.label_anchors(gt, n_gt, wh, rows, cols, voc, 16), args.iters)
+        n = rows * cols * 9
+        rec("label_anchors", "C4 voc 50gt b128", ms, batch, batch * (16 * 50 + n * 18))
+        cu, ip, bb, _ = ops.label_anchors(gt, n_gt, wh, rows, cols, voc, 16)
+        ms = timeit(lambda: ops.pack_rpn_targets(cu, ip, bb, rows, cols, 9), args.iters)
+        rec("pack_rpn_targets", "C4 voc b128", ms, batch, batch * (n * 18 + rows * cols * (18 + 72 * 4)))
+        rois = dev(np.stack([synth.random_rois(2000, rows, cols, 400 + i) for i in range(batch)]))
+        gt64 = dev(gts.astype(np.float64) / 16)
+        gcls = dev(np.tile(np.arange(50, dtype=np.int32) % 20, (batch, 1)))
+        ms = timeit(lambda: ops.label_rois(rois, gt64, gcls, n_gt, 21), args.iters)
+        rec("label_rois", "C4 2000 rois 50gt b128", ms, batch, batch * 2000 * (8 + 8 + 84 + 640 + 4))
+
+    # ---- C2 detector post-processing: 64 images x 320 rows x 21 classes ------------------------------------------------
+    if want("postprocess"):
+        batch = 64
+        rois = dev(np.stack([synth.random_rois(320, 37, 62, 500 + i) for i in range(batch)]))
+        outs = [synth.detector_outputs(320, 21, 600 + i) for i in range(batch)]
+        oc, orr = dev(np.stack([o[0] for o in outs])), dev(np.stack([o[1] for o in outs]))
+        ratio = dev(np.full(batch, 1.6))
+        ms = timeit(lambda: ops.det_postprocess(rois, oc, orr, ratio, 20), args.iters)
+        rec("det_postprocess", "C2 vgg16 320 rows 21 cls b64", ms, batch)
+
+    if args.json:
+        os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
+        json.dump(res, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

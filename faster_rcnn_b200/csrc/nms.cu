@@ -61,7 +61,7 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
                float* __restrict__ keep_scores) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem);
-  int4* kept_box = reinterpret_cast<int4*>(smem + (size_t)buf_elems * 8);
+  int4* kept_box = reinterpret_cast<int4*>(smem + (((size_t)buf_elems * 8 + 15) & ~(size_t)15));
   int* kept_area = reinterpret_cast<int*>(kept_box + max_keep);
   int* kept_slot = kept_area + max_keep;
 
@@ -244,7 +244,7 @@ int launch_nms_i16(frcnn_handle* h, cudaStream_t stream, const int16_t* boxes, c
   while (pow2 < n_max) pow2 <<= 1;
   const int buf_elems = (n_max <= FRCNN_NMS_MAX_UNSORTED) ? pow2 : n_max;
   const int max_keep = max_boxes < n_max ? max_boxes : n_max;
-  const size_t smem = (size_t)buf_elems * 8 + (size_t)max_keep * (16 + 4 + 4) + 16;
+  const size_t smem = align_up((size_t)buf_elems * 8, 16) + (size_t)max_keep * (16 + 4 + 4) + 16;
   if (smem + 2048 > (size_t)h->max_smem_optin)
     return fail(h, FRCNN_ERR_UNSUPPORTED, "nms_i16: n_max/max_boxes need more shared memory than one SM has%s%s");
   void* ws = nullptr;
