@@ -1,13 +1,16 @@
 // K-d: RoI layer (custom_layers.py:35-56) forward and backward, channels-last.
 //
+// A tiny pre-kernel turns the RoIs of a launch into tap tables (all int<->float conversions and
+// divisions of the layer, once per (RoI, output index)); the streaming kernels only index them.
+//
 // Forward (both modes): one CTA per (RoI, 1024-channel block, image); a thread owns four
 // consecutive channels (128-bit loads/stores), walks the PxP outputs and streams them out with
 // evict-first stores.  The feature map (9.8 MB at 38x63x1024) stays L2-resident, the P*P*C
 // outputs (401 MB at N=2000) are the HBM stream.
 //
-// Backward (both modes): spatial-tile ownership.  A CTA owns a 4x8-cell tile of dX for a
-// 256-channel chunk in shared memory, a thread owns its channel columns of it.  RoIs are walked
-// in index order, and inside a RoI the taps / bins in (ph, pw, tap) order, so every addition
+// Backward, resize mode: cell-stationary gather, one warp per dX cell accumulating in registers.
+// Backward, max mode: spatial-tile ownership in shared memory with per-tile work lists.
+// Both walk RoIs in index order and, inside a RoI, bins in (ph, pw, tap) order, so every addition
 // into a given dX element happens in one fixed order: no atomics, bit-reproducible run to run.
 // (oracle/roi_oracle.py sums each RoI into a private crop first, like TF's slice-gradient +
 // AddN, so resize-mode gradients agree to float32 round-off, not bit for bit; max mode is exact.)
@@ -53,45 +56,97 @@ __device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
   return make_float4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t);
 }
 
-constexpr int ROI_FWD_THREADS = 256;
+__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
+// ---------------------------------------------------------------------------------------
+// per-launch RoI tables (tiny pre-kernel): the crop of every RoI and, per output index p, the
+// source taps (resize) or bin bounds (max) of both axes in ABSOLUTE map coordinates.  All integer
+// <-> float conversions and divisions of the layer happen here, once per (RoI, p), instead of
+// once per (RoI, p, channel block) in the streaming kernels (they run on the 16-lane XU pipe).
+//   crops[roi]      = (x1, y1, w, h)
+//   taps[roi*P + p] = resize: (ylo | yhi << 16, bits(ylerp), xlo | xhi << 16, bits(xlerp))
+//                     max:    (ya  | yb  << 16, 0,           xa  | xb  << 16, 0)   [a, b) bounds
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+roi_table_kernel(const void* __restrict__ rois, int dtype, int n_total, int W, int H, int P,
+                 int4* __restrict__ crops, int4* __restrict__ taps) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n_total * (P + 1)) return;
+  const int roi = idx / (P + 1), p = idx - roi * (P + 1);
+  const Crop k = load_crop(rois, dtype, (size_t)roi, W, H);
+  if (p == P) {
+    crops[roi] = make_int4(k.x1, k.y1, k.w, k.h);
+    return;
+  }
+  int4 rec = make_int4(0, 0, 0, 0);
+  if (k.w > 0 && k.h > 0) {
+    if (MODE == FRCNN_ROI_RESIZE) {
+      const Tap ty = axis_tap(p, (float)k.h / (float)P, k.h), tx = axis_tap(p, (float)k.w / (float)P, k.w);
+      rec = make_int4((k.y1 + ty.lo) | ((k.y1 + ty.hi) << 16), __float_as_int(ty.lerp),
+                      (k.x1 + tx.lo) | ((k.x1 + tx.hi) << 16), __float_as_int(tx.lerp));
+    } else {
+      const int ya = k.y1 + (p * k.h) / P, yb = k.y1 + ((p + 1) * k.h + P - 1) / P;
+      const int xa = k.x1 + (p * k.w) / P, xb = k.x1 + ((p + 1) * k.w + P - 1) / P;
+      rec = make_int4(ya | (yb << 16), 0, xa | (xb << 16), 0);
+    }
+  }
+  taps[(size_t)roi * P + p] = rec;
+}
+
+constexpr int ROI_FWD_THREADS = 256;
+constexpr int ROI_MAX_TABLE_P = 32;     // table-driven kernels support pool sizes up to 32
+
+// Forward: one CTA per (RoI, 1024-channel block, image); a thread owns four consecutive channels.
 template <int MODE>
 __global__ void __launch_bounds__(ROI_FWD_THREADS)
-roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* __restrict__ rois, int dtype,
-               int N, int P, float* __restrict__ out, int* __restrict__ argmax) {
+roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const int4* __restrict__ crops,
+               const int4* __restrict__ taps, int N, int P, float* __restrict__ out, int* __restrict__ argmax) {
+  __shared__ int4 s_tap[ROI_MAX_TABLE_P];
+  __shared__ int4 s_crop;
   const int r = blockIdx.x, img = blockIdx.z;
+  const size_t roi = (size_t)img * N + r;
+  if (threadIdx.x < P) s_tap[threadIdx.x] = taps[roi * P + threadIdx.x];
+  if (threadIdx.x == 32) s_crop = crops[roi];
+  __syncthreads();
   const int c = (blockIdx.y * ROI_FWD_THREADS + threadIdx.x) * 4;
   if (c >= C) return;
-  const Crop k = load_crop(rois, dtype, (size_t)img * N + r, W, H);
   const float* f = feat + (size_t)img * H * W * C + c;
-  const size_t obase = (((size_t)img * N + r) * P * P) * C + c;
-  if (k.w <= 0 || k.h <= 0) {   // TF would raise on an empty crop; we emit zeros
+  const size_t obase = (roi * P * P) * C + c;
+  if (s_crop.z <= 0 || s_crop.w <= 0) {   // TF would raise on an empty crop; we emit zeros
     for (int b = 0; b < P * P; ++b) {
       st_cs_f4(out + obase + (size_t)b * C, make_float4(0.f, 0.f, 0.f, 0.f));
       if (MODE == FRCNN_ROI_MAX) st_cs_i4(argmax + obase + (size_t)b * C, make_int4(0, 0, 0, 0));
     }
     return;
   }
+  const size_t row_stride = (size_t)W * C;
   if (MODE == FRCNN_ROI_RESIZE) {
-    const float ys = (float)k.h / (float)P, xs = (float)k.w / (float)P;
     for (int ph = 0; ph < P; ++ph) {
-      const Tap ty = axis_tap(ph, ys, k.h);
-      const float* row_lo = f + (size_t)(k.y1 + ty.lo) * W * C;
-      const float* row_hi = f + (size_t)(k.y1 + ty.hi) * W * C;
+      const int4 ty = s_tap[ph];
+      const float* row_lo = f + (size_t)(ty.x & 0xffff) * row_stride;
+      const float* row_hi = f + (size_t)(ty.x >> 16) * row_stride;
+      const float ly = __int_as_float(ty.y);
+      float* o = out + obase + (size_t)ph * P * C;
+      // Measured and rejected (profiles/roi_fwd_r01.md): issuing the tap loads of 2/4/7 outputs ahead
+      // (no gain: the kernel is bound by L1/TEX + DRAM-write throughput, not load latency) and keeping
+      // the last two source columns in registers (fewer loads, but the extra registers cost more
+      // occupancy than the loads saved).
       for (int pw = 0; pw < P; ++pw) {
-        const Tap tx = axis_tap(pw, xs, k.w);
-        const size_t xl = (size_t)(k.x1 + tx.lo) * C, xh = (size_t)(k.x1 + tx.hi) * C;
+        const int4 tx = s_tap[pw];
+        const size_t xl = (size_t)(tx.z & 0xffff) * C, xh = (size_t)(tx.z >> 16) * C;
+        const float lx = __int_as_float(tx.w);
         const float4 tl = ldg_f4(row_lo + xl), tr = ldg_f4(row_lo + xh);
         const float4 bl = ldg_f4(row_hi + xl), br = ldg_f4(row_hi + xh);
-        const float4 top = lerp4(tl, tr, tx.lerp), bot = lerp4(bl, br, tx.lerp);
-        st_cs_f4(out + obase + (size_t)(ph * P + pw) * C, lerp4(top, bot, ty.lerp));
+        const float4 top = lerp4(tl, tr, lx), bot = lerp4(bl, br, lx);
+        st_cs_f4(o + (size_t)pw * C, lerp4(top, bot, ly));
       }
     }
   } else {
     for (int ph = 0; ph < P; ++ph) {
-      const int ya = k.y1 + (ph * k.h) / P, yb = k.y1 + ((ph + 1) * k.h + P - 1) / P;
+      const int ya = s_tap[ph].x & 0xffff, yb = s_tap[ph].x >> 16;
       for (int pw = 0; pw < P; ++pw) {
-        const int xa = k.x1 + (pw * k.w) / P, xb = k.x1 + ((pw + 1) * k.w + P - 1) / P;
+        const int xa = s_tap[pw].z & 0xffff, xb = s_tap[pw].z >> 16;
         float4 best = ldg_f4(f + ((size_t)ya * W + xa) * C);
         int4 arg = make_int4(ya * W + xa, ya * W + xa, ya * W + xa, ya * W + xa);
         for (int y = ya; y < yb; ++y) {
@@ -170,7 +225,6 @@ constexpr int BT_CH = BT_THREADS * 4;          // channels per CTA
 constexpr int BT_LIST = 1568;                  // work items per RoI chunk (32 RoIs x 49 bins at P = 7)
 constexpr int BT_UNROLL = 4;                   // dY loads in flight per thread
 
-__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ void add4(float4* p, float4 v) {
   float4 a = *p;
   a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -347,8 +401,9 @@ constexpr int CW_WARPS = 8;
 
 template <int CPB>
 __global__ void __launch_bounds__(CW_WARPS * 32)
-roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const void* __restrict__ rois, int dtype, int H, int W,
-                           int C, int N, int P, float* __restrict__ gfeat) {
+roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restrict__ crops,
+                           const int4* __restrict__ taps, int H, int W, int C, int N, int P,
+                           float* __restrict__ gfeat) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cell = blockIdx.x * CW_WARPS + warp;
   if (cell >= H * W) return;                        // warp-uniform; the kernel has no block-level barrier
@@ -356,6 +411,8 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const void* __restric
   const int y = cell / W, x = cell - y * W;
   const int cbase = blockIdx.y * (CPB * 128) + 4 * lane;
   const float* g_img = gout + (size_t)img * N * P * P * C;
+  const int4* crop_img = crops + (size_t)img * N;
+  const int4* tap_img = taps + (size_t)img * N * P;
 
   float4 acc[CPB];
 #pragma unroll
@@ -363,31 +420,28 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const void* __restric
 
   for (int w0 = 0; w0 < N; w0 += 32) {
     const int r = w0 + lane;
-    Crop k = {0, 0, 0, 0};
     bool inside = false;
     if (r < N) {
-      k = load_crop(rois, dtype, (size_t)img * N + r, W, H);
-      inside = k.w > 0 && k.h > 0 && x >= k.x1 && x < k.x1 + k.w && y >= k.y1 && y < k.y1 + k.h;
+      const int4 k = __ldg(crop_img + r);
+      inside = k.z > 0 && k.w > 0 && x >= k.x && x < k.x + k.z && y >= k.y && y < k.y + k.w;
     }
     unsigned m = __ballot_sync(0xffffffffu, inside);
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      const int kx1 = __shfl_sync(0xffffffffu, k.x1, b), ky1 = __shfl_sync(0xffffffffu, k.y1, b);
-      const int kw = __shfl_sync(0xffffffffu, k.w, b), kh = __shfl_sync(0xffffffffu, k.h, b);
-      const int yy = y - ky1, xx = x - kx1;
-      // lane p computes tap p of both axes; code bit0 = "lo tap is this cell", bit1 = "hi tap is this cell"
+      // lane p looks at tap p of both axes; code bit0 = "lo tap is this cell", bit1 = "hi tap is this cell"
       int ycode = 0, xcode = 0;
       float ly = 0.f, lx = 0.f;
       if (lane < P) {
-        const Tap ty = axis_tap(lane, (float)kh / (float)P, kh), tx = axis_tap(lane, (float)kw / (float)P, kw);
-        ycode = (ty.lo == yy ? 1 : 0) | (ty.hi == yy ? 2 : 0);
-        xcode = (tx.lo == xx ? 1 : 0) | (tx.hi == xx ? 2 : 0);
-        ly = ty.lerp;
-        lx = tx.lerp;
+        const int4 t = __ldg(tap_img + (size_t)(w0 + b) * P + lane);
+        ycode = ((t.x & 0xffff) == y ? 1 : 0) | ((t.x >> 16) == y ? 2 : 0);
+        xcode = ((t.z & 0xffff) == x ? 1 : 0) | ((t.z >> 16) == x ? 2 : 0);
+        ly = __int_as_float(t.y);
+        lx = __int_as_float(t.w);
       }
       unsigned my = __ballot_sync(0xffffffffu, ycode != 0);
       const unsigned mx = __ballot_sync(0xffffffffu, xcode != 0);
+      if (mx == 0u) continue;
       const size_t roi_row = (size_t)(w0 + b) * P;
       while (my) {
         const int ph = __ffs(my) - 1;
@@ -503,15 +557,37 @@ roi_bwd_scalar_kernel(const float* __restrict__ gout, const void* __restrict__ r
       dst[((size_t)y * W + x) * C] = acc[((y - ty0) * BWD_TILE + (x - tx0)) * BWD_CH + threadIdx.x];
 }
 
+// builds the per-launch RoI tables in the handle's scratch arena
+static int build_tables(frcnn_handle* h, cudaStream_t stream, int mode, const void* rois, int dtype, int n_total,
+                        int W, int H, int P, int4** crops, int4** taps) {
+  void *pc = nullptr, *pt = nullptr;
+  int rc = arena_get(h, stream, (size_t)n_total * sizeof(int4), &pc);
+  if (rc) return rc;
+  if ((rc = arena_get(h, stream, (size_t)n_total * P * sizeof(int4), &pt))) return rc;
+  *crops = static_cast<int4*>(pc);
+  *taps = static_cast<int4*>(pt);
+  const int blocks = (int)(((size_t)n_total * (P + 1) + 255) / 256);
+  if (mode == FRCNN_ROI_RESIZE)
+    roi_table_kernel<FRCNN_ROI_RESIZE><<<blocks, 256, 0, stream>>>(rois, dtype, n_total, W, H, P, *crops, *taps);
+  else
+    roi_table_kernel<FRCNN_ROI_MAX><<<blocks, 256, 0, stream>>>(rois, dtype, n_total, W, H, P, *crops, *taps);
+  FRCNN_LAUNCH_CHECK(h, "roi_table_kernel");
+  return FRCNN_OK;
+}
+
 int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* feat, int H, int W, int C,
                    const void* rois, int dtype, int N, int P, int batch, float* out, int32_t* argmax) {
-  if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+  if (C % 4 == 0 && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768 && (reinterpret_cast<uintptr_t>(feat) % 16 == 0) &&
+      (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
       (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0)) {
+    int4 *crops = nullptr, *taps = nullptr;
+    int rc = build_tables(h, stream, mode, rois, dtype, batch * N, W, H, P, &crops, &taps);
+    if (rc) return rc;
     dim3 grid(N, (C / 4 + ROI_FWD_THREADS - 1) / ROI_FWD_THREADS, batch);
     if (mode == FRCNN_ROI_RESIZE)
-      roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, out, argmax);
+      roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, crops, taps, N, P, out, argmax);
     else
-      roi_fwd_kernel<FRCNN_ROI_MAX><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, out, argmax);
+      roi_fwd_kernel<FRCNN_ROI_MAX><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, crops, taps, N, P, out, argmax);
   } else {
     dim3 grid(N, (C + 127) / 128, batch);
     if (mode == FRCNN_ROI_RESIZE)
@@ -527,14 +603,17 @@ int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
                    const int32_t* argmax, int H, int W, int C, int N, int P, int batch, float* gfeat) {
   const int chunk = (P * P <= BT_LIST) ? (BT_LIST / (P * P) < BT_THREADS ? BT_LIST / (P * P) : BT_THREADS) : 0;
   const bool aligned = (reinterpret_cast<uintptr_t>(gout) % 16 == 0) && (reinterpret_cast<uintptr_t>(gfeat) % 16 == 0);
-  if (mode == FRCNN_ROI_RESIZE && C % 4 == 0 && aligned && P <= 32) {
+  if (mode == FRCNN_ROI_RESIZE && C % 4 == 0 && aligned && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768) {
+    int4 *crops = nullptr, *taps = nullptr;
+    int rc = build_tables(h, stream, mode, rois, dtype, batch * N, W, H, P, &crops, &taps);
+    if (rc) return rc;
     const int blocks128 = (C + 127) / 128;
     const int cpb = blocks128 >= 8 ? 8 : (blocks128 >= 4 ? 4 : (blocks128 >= 2 ? 2 : 1));
     dim3 grid((H * W + CW_WARPS - 1) / CW_WARPS, (blocks128 + cpb - 1) / cpb, batch);
-    if (cpb == 8) roi_bwd_resize_cell_kernel<8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, rois, dtype, H, W, C, N, P, gfeat);
-    else if (cpb == 4) roi_bwd_resize_cell_kernel<4><<<grid, CW_WARPS * 32, 0, stream>>>(gout, rois, dtype, H, W, C, N, P, gfeat);
-    else if (cpb == 2) roi_bwd_resize_cell_kernel<2><<<grid, CW_WARPS * 32, 0, stream>>>(gout, rois, dtype, H, W, C, N, P, gfeat);
-    else roi_bwd_resize_cell_kernel<1><<<grid, CW_WARPS * 32, 0, stream>>>(gout, rois, dtype, H, W, C, N, P, gfeat);
+    if (cpb == 8) roi_bwd_resize_cell_kernel<8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
+    else if (cpb == 4) roi_bwd_resize_cell_kernel<4><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
+    else if (cpb == 2) roi_bwd_resize_cell_kernel<2><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
+    else roi_bwd_resize_cell_kernel<1><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
     FRCNN_LAUNCH_CHECK(h, "roi_bwd_resize_cell_kernel");
     return FRCNN_OK;
   }
