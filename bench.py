@@ -251,8 +251,7 @@ def run_ours(args, rank, world, local_rank):
             if "rois" not in gathered:
                 gathered["rois"] = torch.empty((world * batch, MAX_BOXES, 4), dtype=torch.int16, device=dev)
                 gathered["count"] = torch.empty((world * batch,), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gathered["rois"], rois)
-            dist.all_gather_into_tensor(gathered["count"], count)
+            parallel.all_gather_rois(rois, count, gathered["rois"], gathered["count"])
         return rois, count, pooled
 
     from faster_rcnn_b200 import ops as pipe_ops
@@ -292,8 +291,7 @@ def run_ours(args, rank, world, local_rank):
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     def exchange(rois, scores, count):
         if world > 1:
-            dist.all_gather_into_tensor(gathered["rois"], rois)
-            dist.all_gather_into_tensor(gathered["count"], count)
+            parallel.all_gather_rois(rois, count, gathered["rois"], gathered["count"])
 
     e_start.record()
     for _ in range(args.steps):

@@ -54,3 +54,19 @@ def all_gather_detections(dets, counts, group=None):
     dist.all_gather_into_tensor(out_d, dets.contiguous(), group=group)
     dist.all_gather_into_tensor(out_c, counts.contiguous(), group=group)
     return out_d, out_c
+
+
+def all_gather_rois(rois, count, out_rois=None, out_count=None, group=None):
+    """All-gather of the proposal stage's result: rois (b,max_boxes,4) int16 + count (b,) int32 ->
+    (world*b, max_boxes, 4) int16, (world*b,) int32.  NCCL has no int16 type, so the RoI rows travel
+    as int32 pairs (a reinterpreting view, no copy).  `out_*` may be preallocated buffers."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return rois, count
+    world = dist.get_world_size(group)
+    if out_rois is None:
+        out_rois = torch.empty((world * rois.shape[0],) + tuple(rois.shape[1:]), dtype=rois.dtype, device=rois.device)
+    if out_count is None:
+        out_count = torch.empty((world * count.shape[0],), dtype=count.dtype, device=count.device)
+    dist.all_gather_into_tensor(out_rois.view(torch.int32), rois.contiguous().view(torch.int32), group=group)
+    dist.all_gather_into_tensor(out_count, count.contiguous(), group=group)
+    return out_rois, out_count
