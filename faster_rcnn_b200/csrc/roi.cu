@@ -8,8 +8,7 @@
 // evict-first stores.  The feature map (9.8 MB at 38x63x1024) stays L2-resident, the P*P*C
 // outputs (401 MB at N=2000) are the HBM stream.
 //
-// Backward, resize mode: cell-stationary gather, one warp per dX cell accumulating in registers.
-// Backward, max mode: spatial-tile ownership in shared memory with per-tile work lists.
+// Backward (both modes): cell-stationary gather, one warp per dX cell accumulating in registers.
 // Both walk RoIs in index order and, inside a RoI, bins in (ph, pw, tap) order, so every addition
 // into a given dX element happens in one fixed order: no atomics, bit-reproducible run to run.
 // (oracle/roi_oracle.py sums each RoI into a private crop first, like TF's slice-gradient +
@@ -209,182 +208,6 @@ __global__ void roi_fwd_scalar_kernel(const float* __restrict__ feat, int H, int
 }
 
 // ---------------------------------------------------------------------------------------
-// backward: spatial-tile ownership, work lists, float4 channel columns
-//
-// A CTA owns a 4x8-cell tile of dX for 256 channels in shared memory; a thread owns one float4
-// (resize) / four strided (max) channel columns of it, so no two threads ever touch the same
-// accumulator: no atomics, no barriers in the accumulation loop, one fixed summation order.
-// RoIs are taken in chunks: one thread per RoI finds the contiguous (ph, pw) ranges whose taps /
-// bins can touch the tile, an ordered block scan turns the counts into offsets, and the
-// (roi, ph, pw) work items land in a shared list in ascending (roi, ph, pw) order.  Then every
-// thread streams through the list, issuing the dY loads of several items before consuming them.
-// ---------------------------------------------------------------------------------------
-constexpr int BT_H = 4, BT_W = 8, BT_CELLS = BT_H * BT_W;
-constexpr int BT_THREADS = 64;
-constexpr int BT_CH = BT_THREADS * 4;          // channels per CTA
-constexpr int BT_LIST = 1568;                  // work items per RoI chunk (32 RoIs x 49 bins at P = 7)
-constexpr int BT_UNROLL = 4;                   // dY loads in flight per thread
-
-__device__ __forceinline__ void add4(float4* p, float4 v) {
-  float4 a = *p;
-  a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-  *p = a;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(BT_THREADS)
-roi_bwd_tile_kernel(const float* __restrict__ gout, const void* __restrict__ rois, int dtype,
-                    const int* __restrict__ argmax, int H, int W, int C, int N, int P, int tiles_x, int chunk,
-                    float* __restrict__ gfeat) {
-  __shared__ __align__(16) float s_acc[BT_CELLS * BT_CH];
-  __shared__ unsigned s_list[BT_LIST];
-  __shared__ int4 s_crop[BT_THREADS];
-  __shared__ float2 s_scale[BT_THREADS];
-  __shared__ int s_wtot[BT_THREADS / 32];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, img = blockIdx.z;
-  const int ty0 = (tile / tiles_x) * BT_H, tx0 = (tile % tiles_x) * BT_W;
-  const int th = min(BT_H, H - ty0), tw = min(BT_W, W - tx0);
-  const int cbase = blockIdx.y * BT_CH;
-  for (int i = tid; i < BT_CELLS * BT_CH; i += BT_THREADS) s_acc[i] = 0.f;
-
-  const size_t img_off = (size_t)img * N * P * P * C;
-  const float* g_img = gout + img_off;
-  const int* a_img = (MODE == FRCNN_ROI_MAX) ? argmax + img_off : nullptr;
-  const int c4 = cbase + 4 * tid;                 // resize: four consecutive channels
-  const bool live4 = c4 < C;
-  float4* acc4 = reinterpret_cast<float4*>(s_acc) + tid;      // cell stride = BT_THREADS float4
-
-  for (int base = 0; base < N; base += chunk) {
-    // ---- build the work list of this RoI chunk (thread t <-> RoI base + t) ----
-    int pa = 0, pb = 0, qa = 0, qb = 0;
-    if (tid < chunk && base + tid < N) {
-      const Crop k = load_crop(rois, dtype, (size_t)img * N + base + tid, W, H);
-      s_crop[tid] = make_int4(k.x1, k.y1, k.w, k.h);
-      if (k.w > 0 && k.h > 0 && k.x1 < tx0 + tw && k.x1 + k.w > tx0 && k.y1 < ty0 + th && k.y1 + k.h > ty0) {
-        const float ys = (float)k.h / (float)P, xs = (float)k.w / (float)P;
-        s_scale[tid] = make_float2(ys, xs);
-        pa = P; qa = P;
-        for (int p = 0; p < P; ++p) {
-          bool hy, hx;
-          if (MODE == FRCNN_ROI_RESIZE) {
-            const Tap t = axis_tap(p, ys, k.h), u = axis_tap(p, xs, k.w);
-            hy = (unsigned)(k.y1 + t.lo - ty0) < (unsigned)th || (unsigned)(k.y1 + t.hi - ty0) < (unsigned)th;
-            hx = (unsigned)(k.x1 + u.lo - tx0) < (unsigned)tw || (unsigned)(k.x1 + u.hi - tx0) < (unsigned)tw;
-          } else {
-            hy = k.y1 + (p * k.h) / P < ty0 + th && k.y1 + ((p + 1) * k.h + P - 1) / P > ty0;
-            hx = k.x1 + (p * k.w) / P < tx0 + tw && k.x1 + ((p + 1) * k.w + P - 1) / P > tx0;
-          }
-          if (hy) { pa = min(pa, p); pb = p + 1; }
-          if (hx) { qa = min(qa, p); qb = p + 1; }
-        }
-        if (pb == 0 || qb == 0) { pa = pb = qa = qb = 0; }
-      }
-    }
-    const int cnt = (pb - pa) * (qb - qa);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
-    }
-    if (lane == 31) s_wtot[warp] = incl;
-    __syncthreads();
-    int off = incl - cnt, total = 0;
-#pragma unroll
-    for (int w = 0; w < BT_THREADS / 32; ++w) {
-      if (w < warp) off += s_wtot[w];
-      total += s_wtot[w];
-    }
-    for (int ph = pa; ph < pb; ++ph)
-      for (int pw = qa; pw < qb; ++pw) s_list[off++] = ((unsigned)tid << 16) | ((unsigned)ph << 8) | (unsigned)pw;
-    __syncthreads();
-
-    // ---- consume: every thread walks the whole list for its own channel columns ----
-    if (MODE == FRCNN_ROI_RESIZE) {
-      for (int i0 = 0; i0 < total; i0 += BT_UNROLL) {
-        float4 g[BT_UNROLL];
-        unsigned e[BT_UNROLL];
-#pragma unroll
-        for (int u = 0; u < BT_UNROLL; ++u) {
-          g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          e[u] = 0u;
-          if (i0 + u < total) {
-            e[u] = s_list[i0 + u];
-            const int r = base + (int)(e[u] >> 16), ph = (e[u] >> 8) & 255, pw = e[u] & 255;
-            if (live4) g[u] = ldg_f4(g_img + ((size_t)(r * P + ph) * P + pw) * C + c4);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < BT_UNROLL; ++u) {
-          if (i0 + u < total) {
-            const int t = (int)(e[u] >> 16), ph = (e[u] >> 8) & 255, pw = e[u] & 255;
-            const int4 k = s_crop[t];
-            const float2 sc = s_scale[t];
-            const Tap ty = axis_tap(ph, sc.x, k.w), tx = axis_tap(pw, sc.y, k.z);
-            const int ylo = k.y + ty.lo - ty0, yhi = k.y + ty.hi - ty0;
-            const int xlo = k.x + tx.lo - tx0, xhi = k.x + tx.hi - tx0;
-            const bool rlo = (unsigned)ylo < (unsigned)th, rhi = (unsigned)yhi < (unsigned)th;
-            const bool clo = (unsigned)xlo < (unsigned)tw, chi = (unsigned)xhi < (unsigned)tw;
-            // order TL, TR, BL, BR; weight product (g*wy)*wx as in ResizeBilinearGrad
-            const float4 gy0 = scale4(g[u], 1.0f - ty.lerp), gy1 = scale4(g[u], ty.lerp);
-            const float wx0 = 1.0f - tx.lerp, wx1 = tx.lerp;
-            if (rlo && clo) add4(acc4 + (ylo * BT_W + xlo) * BT_THREADS, scale4(gy0, wx0));
-            if (rlo && chi) add4(acc4 + (ylo * BT_W + xhi) * BT_THREADS, scale4(gy0, wx1));
-            if (rhi && clo) add4(acc4 + (yhi * BT_W + xlo) * BT_THREADS, scale4(gy1, wx0));
-            if (rhi && chi) add4(acc4 + (yhi * BT_W + xhi) * BT_THREADS, scale4(gy1, wx1));
-          }
-        }
-      }
-    } else {
-      // max mode: the arg-max cell differs per channel; channels are strided (c = cbase + j*64 + tid)
-      // so that both the global loads and the shared-memory columns are conflict-free.
-      const int first = ty0 * W + tx0;
-      for (int i = 0; i < total; ++i) {
-        const unsigned e = s_list[i];
-        const int r = base + (int)(e >> 16), ph = (e >> 8) & 255, pw = e & 255;
-        const size_t o = ((size_t)(r * P + ph) * P + pw) * C;
-        int a[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = cbase + j * BT_THREADS + tid;
-          a[j] = (c < C) ? __ldg(a_img + o + c) : -1;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = cbase + j * BT_THREADS + tid;
-          int cell = -1;
-#pragma unroll
-          for (int y = 0; y < BT_H; ++y) {
-            const int d = a[j] - (first + y * W);
-            if (y < th && (unsigned)d < (unsigned)tw) cell = y * BT_W + d;
-          }
-          if (cell >= 0 && a[j] >= 0) s_acc[cell * BT_CH + j * BT_THREADS + tid] += __ldg(g_img + o + c);
-        }
-      }
-    }
-    __syncthreads();      // the list and crop tables are rewritten by the next chunk
-  }
-
-  float* dst = gfeat + (size_t)img * H * W * C;
-  if (MODE == FRCNN_ROI_RESIZE) {
-    if (!live4) return;
-    for (int y = 0; y < th; ++y)
-      for (int x = 0; x < tw; ++x)
-        *reinterpret_cast<float4*>(dst + ((size_t)(ty0 + y) * W + tx0 + x) * C + c4) = acc4[(y * BT_W + x) * BT_THREADS];
-  } else {
-    for (int y = 0; y < th; ++y)
-      for (int x = 0; x < tw; ++x)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = cbase + j * BT_THREADS + tid;
-          if (c < C) dst[((size_t)(ty0 + y) * W + tx0 + x) * C + c] = s_acc[(y * BT_W + x) * BT_CH + j * BT_THREADS + tid];
-        }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // backward, resize mode: cell-stationary gather, one warp per dX cell
 //
 // A warp owns one feature-map cell (y, x) for up to 1024 channels (lane l holds float4 channel
@@ -398,6 +221,32 @@ roi_bwd_tile_kernel(const float* __restrict__ gout, const void* __restrict__ roi
 // same CTA (x direction) or the same wave (y direction), so the re-reads hit L1 / L2, not DRAM.
 // ---------------------------------------------------------------------------------------
 constexpr int CW_WARPS = 8;
+// Measured and rejected (profiles/): queueing the contributions per warp in shared memory and streaming
+// them with a two-deep software pipeline (2.1 ms vs 1.34 ms at C1 x 64 images): separating the integer
+// "collect" phase from the load phase removes the overlap that independent warps get for free.
+
+template <int CPB>
+__device__ __forceinline__ void cell_accumulate(int yc, int xc, float wy1, float wx1, const float4 (&g)[CPB],
+                                                float4 (&acc)[CPB]) {
+  const float wy0 = 1.0f - wy1, wx0 = 1.0f - wx1;
+  // Taps in the order TL, TR, BL, BR.  The four conditions are warp-uniform and sit outside the channel
+  // loop (4 branches per bin).  The tap weight wy*wx is formed once per bin and applied with one FMA per
+  // element: resize-mode gradients are a tolerance comparison anyway (fixed but different summation order
+  // than TF's slice-grad + AddN; TF's own GPU kernel uses atomics), and this cuts the FP instruction count 3x.
+#define FRCNN_CELL_ACCUM(WY, WX)                                                              \
+  {                                                                                            \
+    const float wgt = __fmul_rn(WY, WX);                                                       \
+    _Pragma("unroll") for (int j = 0; j < CPB; ++j) {                                          \
+      acc[j].x = __fmaf_rn(g[j].x, wgt, acc[j].x); acc[j].y = __fmaf_rn(g[j].y, wgt, acc[j].y); \
+      acc[j].z = __fmaf_rn(g[j].z, wgt, acc[j].z); acc[j].w = __fmaf_rn(g[j].w, wgt, acc[j].w); \
+    }                                                                                          \
+  }
+  if ((yc & 1) && (xc & 1)) FRCNN_CELL_ACCUM(wy0, wx0)
+  if ((yc & 1) && (xc & 2)) FRCNN_CELL_ACCUM(wy0, wx1)
+  if ((yc & 2) && (xc & 1)) FRCNN_CELL_ACCUM(wy1, wx0)
+  if ((yc & 2) && (xc & 2)) FRCNN_CELL_ACCUM(wy1, wx1)
+#undef FRCNN_CELL_ACCUM
+}
 
 template <int CPB>
 __global__ void __launch_bounds__(CW_WARPS * 32)
@@ -411,6 +260,88 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
   const int y = cell / W, x = cell - y * W;
   const int cbase = blockIdx.y * (CPB * 128) + 4 * lane;
   const float* g_img = gout + (size_t)img * N * P * P * C;
+  const int4* crop_img = crops + (size_t)img * N;
+  const int4* tap_img = taps + (size_t)img * N * P;
+  float4 acc[CPB];
+#pragma unroll
+  for (int j = 0; j < CPB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int w0 = 0; w0 < N; w0 += 32) {
+    const int r = w0 + lane;
+    bool inside = false;
+    if (r < N) {
+      const int4 k = __ldg(crop_img + r);
+      inside = k.z > 0 && k.w > 0 && x >= k.x && x < k.x + k.z && y >= k.y && y < k.y + k.w;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, inside);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      // lane p looks at tap p of both axes; code bit0 = "lo tap is this cell", bit1 = "hi tap is this cell"
+      int ycode = 0, xcode = 0;
+      int lyb = 0, lxb = 0;
+      if (lane < P) {
+        const int4 t = __ldg(tap_img + (size_t)(w0 + b) * P + lane);
+        ycode = ((t.x & 0xffff) == y ? 1 : 0) | ((t.x >> 16) == y ? 2 : 0);
+        xcode = ((t.z & 0xffff) == x ? 1 : 0) | ((t.z >> 16) == x ? 2 : 0);
+        lyb = t.y;
+        lxb = t.w;
+      }
+      unsigned my = __ballot_sync(0xffffffffu, ycode != 0);
+      const unsigned mx = __ballot_sync(0xffffffffu, xcode != 0);
+      if (mx == 0u) continue;
+      const int roi_row = (w0 + b) * P;
+      while (my) {
+        const int ph = __ffs(my) - 1;
+        my &= my - 1;
+        const int yc = __shfl_sync(0xffffffffu, ycode, ph);
+        const int wyb = __shfl_sync(0xffffffffu, lyb, ph);
+        unsigned mxx = mx;
+        while (mxx) {
+          const int pw = __ffs(mxx) - 1;
+          mxx &= mxx - 1;
+          const int xc = __shfl_sync(0xffffffffu, xcode, pw);
+          const int wxb = __shfl_sync(0xffffffffu, lxb, pw);
+          const float* row = g_img + (size_t)((roi_row + ph) * P + pw) * C + cbase;
+          float4 g[CPB];
+#pragma unroll
+          for (int j = 0; j < CPB; ++j)
+            g[j] = (cbase + j * 128 < C) ? ldg_f4(row + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          cell_accumulate<CPB>(yc, xc, __int_as_float(wyb), __int_as_float(wxb), g, acc);
+        }
+      }
+    }
+  }
+  float* dst = gfeat + ((size_t)img * H * W + cell) * C + cbase;
+#pragma unroll
+  for (int j = 0; j < CPB; ++j)
+    if (cbase + j * 128 < C) *reinterpret_cast<float4*>(dst + j * 128) = acc[j];
+}
+
+// ---------------------------------------------------------------------------------------
+// backward, max mode: the same cell-stationary gather.  A bin (ph, pw) of a RoI can route its
+// gradient to this cell only if the bin covers it, so the warp visits the covering bins in
+// ascending (roi, ph, pw) order, reads the bin's arg-max row (int4 per lane and channel block),
+// and adds dY where the arg-max equals this cell -- the order of oracle roi_max_bwd, bit for bit.
+// The arg-max row of a bin is re-read by every cell the bin covers (L2 hits); dY is read only by
+// the lanes whose channels actually selected this cell.
+// (A shared-memory tile-ownership kernel with per-tile work lists was the first version: 11.9 ms at
+// C1 x 64 images against 2.x ms for this one -- serial LDS/FADD/STS chains and 8 warps per SM.)
+// ---------------------------------------------------------------------------------------
+template <int CPB>
+__global__ void __launch_bounds__(CW_WARPS * 32)
+roi_bwd_max_cell_kernel(const float* __restrict__ gout, const int* __restrict__ argmax,
+                        const int4* __restrict__ crops, const int4* __restrict__ taps, int H, int W, int C, int N,
+                        int P, float* __restrict__ gfeat) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cell = blockIdx.x * CW_WARPS + warp;
+  if (cell >= H * W) return;
+  const int img = blockIdx.z;
+  const int y = cell / W, x = cell - y * W;
+  const int cbase = blockIdx.y * (CPB * 128) + 4 * lane;
+  const size_t img_off = (size_t)img * N * P * P * C;
+  const float* g_img = gout + img_off;
+  const int* a_img = argmax + img_off;
   const int4* crop_img = crops + (size_t)img * N;
   const int4* tap_img = taps + (size_t)img * N * P;
 
@@ -429,48 +360,35 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      // lane p looks at tap p of both axes; code bit0 = "lo tap is this cell", bit1 = "hi tap is this cell"
-      int ycode = 0, xcode = 0;
-      float ly = 0.f, lx = 0.f;
+      bool hy = false, hx = false;
       if (lane < P) {
         const int4 t = __ldg(tap_img + (size_t)(w0 + b) * P + lane);
-        ycode = ((t.x & 0xffff) == y ? 1 : 0) | ((t.x >> 16) == y ? 2 : 0);
-        xcode = ((t.z & 0xffff) == x ? 1 : 0) | ((t.z >> 16) == x ? 2 : 0);
-        ly = __int_as_float(t.y);
-        lx = __int_as_float(t.w);
+        hy = y >= (t.x & 0xffff) && y < (t.x >> 16);
+        hx = x >= (t.z & 0xffff) && x < (t.z >> 16);
       }
-      unsigned my = __ballot_sync(0xffffffffu, ycode != 0);
-      const unsigned mx = __ballot_sync(0xffffffffu, xcode != 0);
-      if (mx == 0u) continue;
-      const size_t roi_row = (size_t)(w0 + b) * P;
+      unsigned my = __ballot_sync(0xffffffffu, hy);
+      const unsigned mx = __ballot_sync(0xffffffffu, hx);
+      const int roi_row = (w0 + b) * P;
       while (my) {
         const int ph = __ffs(my) - 1;
         my &= my - 1;
-        const int yc = __shfl_sync(0xffffffffu, ycode, ph);
-        const float wy1 = __shfl_sync(0xffffffffu, ly, ph), wy0 = 1.0f - wy1;
         unsigned mxx = mx;
         while (mxx) {
           const int pw = __ffs(mxx) - 1;
           mxx &= mxx - 1;
-          const int xc = __shfl_sync(0xffffffffu, xcode, pw);
-          const float wx1 = __shfl_sync(0xffffffffu, lx, pw), wx0 = 1.0f - wx1;
-          const float* row = g_img + ((roi_row + ph) * P + pw) * C + cbase;
-          float4 g[CPB];
+          const size_t o = (size_t)((roi_row + ph) * P + pw) * C + cbase;
+          int4 a[CPB];
 #pragma unroll
           for (int j = 0; j < CPB; ++j)
-            g[j] = (cbase + j * 128 < C) ? ldg_f4(row + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[j] = (cbase + j * 128 < C) ? __ldg(reinterpret_cast<const int4*>(a_img + o + j * 128)) : make_int4(-1, -1, -1, -1);
 #pragma unroll
           for (int j = 0; j < CPB; ++j) {
-            // order TL, TR, BL, BR; weight product (g*wy)*wx as in ResizeBilinearGrad
-            if (yc & 1) {
-              const float4 t = scale4(g[j], wy0);
-              if (xc & 1) { const float4 v = scale4(t, wx0); acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w; }
-              if (xc & 2) { const float4 v = scale4(t, wx1); acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w; }
-            }
-            if (yc & 2) {
-              const float4 t = scale4(g[j], wy1);
-              if (xc & 1) { const float4 v = scale4(t, wx0); acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w; }
-              if (xc & 2) { const float4 v = scale4(t, wx1); acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w; }
+            if (a[j].x == cell || a[j].y == cell || a[j].z == cell || a[j].w == cell) {
+              const float4 g = ldg_f4(g_img + o + j * 128);
+              if (a[j].x == cell) acc[j].x += g.x;
+              if (a[j].y == cell) acc[j].y += g.y;
+              if (a[j].z == cell) acc[j].z += g.z;
+              if (a[j].w == cell) acc[j].w += g.w;
             }
           }
         }
@@ -601,30 +519,26 @@ int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
 
 int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* gout, const void* rois, int dtype,
                    const int32_t* argmax, int H, int W, int C, int N, int P, int batch, float* gfeat) {
-  const int chunk = (P * P <= BT_LIST) ? (BT_LIST / (P * P) < BT_THREADS ? BT_LIST / (P * P) : BT_THREADS) : 0;
-  const bool aligned = (reinterpret_cast<uintptr_t>(gout) % 16 == 0) && (reinterpret_cast<uintptr_t>(gfeat) % 16 == 0);
-  if (mode == FRCNN_ROI_RESIZE && C % 4 == 0 && aligned && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(gout) % 16 == 0) && (reinterpret_cast<uintptr_t>(gfeat) % 16 == 0) &&
+                       (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0);
+  if (C % 4 == 0 && aligned && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768) {
     int4 *crops = nullptr, *taps = nullptr;
     int rc = build_tables(h, stream, mode, rois, dtype, batch * N, W, H, P, &crops, &taps);
     if (rc) return rc;
     const int blocks128 = (C + 127) / 128;
-    const int cpb = blocks128 >= 8 ? 8 : (blocks128 >= 4 ? 4 : (blocks128 >= 2 ? 2 : 1));
+    // channel blocks per warp: 8 (one warp per cell at C = 1024) when the launch has enough cells to fill
+    // the GPU, else 4 so that a single image still yields >= 32 warps per SM
+    int cpb = blocks128 >= 8 ? 8 : (blocks128 >= 4 ? 4 : (blocks128 >= 2 ? 2 : 1));
+    if (cpb == 8 && (long long)H * W * batch < 2LL * h->sm_count * 32) cpb = 4;
     dim3 grid((H * W + CW_WARPS - 1) / CW_WARPS, (blocks128 + cpb - 1) / cpb, batch);
-    if (cpb == 8) roi_bwd_resize_cell_kernel<8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
-    else if (cpb == 4) roi_bwd_resize_cell_kernel<4><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
-    else if (cpb == 2) roi_bwd_resize_cell_kernel<2><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
-    else roi_bwd_resize_cell_kernel<1><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);
-    FRCNN_LAUNCH_CHECK(h, "roi_bwd_resize_cell_kernel");
-    return FRCNN_OK;
-  }
-  if (C % 4 == 0 && aligned && chunk > 0 && P <= 255) {
-    const int tiles_x = (W + BT_W - 1) / BT_W, tiles_y = (H + BT_H - 1) / BT_H;
-    dim3 grid(tiles_x * tiles_y, (C + BT_CH - 1) / BT_CH, batch);
-    if (mode == FRCNN_ROI_RESIZE)
-      roi_bwd_tile_kernel<FRCNN_ROI_RESIZE><<<grid, BT_THREADS, 0, stream>>>(gout, rois, dtype, argmax, H, W, C, N, P, tiles_x, chunk, gfeat);
-    else
-      roi_bwd_tile_kernel<FRCNN_ROI_MAX><<<grid, BT_THREADS, 0, stream>>>(gout, rois, dtype, argmax, H, W, C, N, P, tiles_x, chunk, gfeat);
-    FRCNN_LAUNCH_CHECK(h, "roi_bwd_tile_kernel");
+#define FRCNN_LAUNCH_CELL(CPB)                                                                                      \
+  if (mode == FRCNN_ROI_RESIZE)                                                                                     \
+    roi_bwd_resize_cell_kernel<CPB><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);    \
+  else                                                                                                              \
+    roi_bwd_max_cell_kernel<CPB><<<grid, CW_WARPS * 32, 0, stream>>>(gout, argmax, crops, taps, H, W, C, N, P, gfeat);
+    if (cpb == 8) { FRCNN_LAUNCH_CELL(8) } else if (cpb == 4) { FRCNN_LAUNCH_CELL(4) } else if (cpb == 2) { FRCNN_LAUNCH_CELL(2) } else { FRCNN_LAUNCH_CELL(1) }
+#undef FRCNN_LAUNCH_CELL
+    FRCNN_LAUNCH_CHECK(h, "roi_bwd_cell_kernel");
     return FRCNN_OK;
   }
   const int tiles_x = (W + BWD_TILE - 1) / BWD_TILE, tiles_y = (H + BWD_TILE - 1) / BWD_TILE;
