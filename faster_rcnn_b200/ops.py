@@ -26,6 +26,12 @@ def _chk(t, dtype, name, ndim=None):
     return t.contiguous()
 
 
+def _chk_out(t, dtype, name, ndim):
+    if not t.is_contiguous():
+        raise ValueError("%s is written in place and must be contiguous" % name)
+    return _chk(t, dtype, name, ndim)
+
+
 def decode_topk(regr, cls, anchor_dims, stride, k, want_dense=False):
     """K-a.  regr (B,R,C,4A) f32, cls (B,R,C,A) f32 -> boxes (B,k,4) i16, scores (B,k) f32,
     index (B,k) i32, count (B,) i32 [, dense (B,R*C*A,4) f32].  det_util.py:63-76,145-155,370-380."""
@@ -77,9 +83,10 @@ def nms_f64(boxes, scores, seg_offsets, max_seg_len, overlap_thresh=0.5, max_box
     return ki, kc
 
 
-def proposals(regr, cls, anchor_dims, stride, k, overlap_thresh=0.7, max_boxes=300):
+def proposals(regr, cls, anchor_dims, stride, k, overlap_thresh=0.7, max_boxes=300, out=None):
     """K-a -> K-b fused on the device.  Returns rois (B,max_boxes,4) i16, scores (B,max_boxes) f32,
-    count (B,) i32.  det_util.py:63-77 (k=12000, 2000) / :136-158 (k=8000, 300)."""
+    count (B,) i32 (written into `out` = (rois, scores, count) when given).
+    det_util.py:63-77 (k=12000, 2000) / :136-158 (k=8000, 300)."""
     regr, cls = _chk(regr, torch.float32, "regr", 4), _chk(cls, torch.float32, "cls", 4)
     ctx = get_context(regr.device)
     b, rows, cols, a = cls.shape
@@ -89,8 +96,14 @@ def proposals(regr, cls, anchor_dims, stride, k, overlap_thresh=0.7, max_boxes=3
     if n_anc != a:
         raise ValueError("cls has %d anchors per cell, anchor_dims has %d" % (a, n_anc))
     max_boxes = int(max_boxes)
-    rois, scores = ctx.empty((b, max_boxes, 4), torch.int16), ctx.empty((b, max_boxes), torch.float32)
-    count = ctx.empty((b,), torch.int32)
+    if out is not None:
+        rois, scores, count = (_chk_out(out[0], torch.int16, "out rois", 3), _chk_out(out[1], torch.float32, "out scores", 2),
+                               _chk_out(out[2], torch.int32, "out count", 1))
+        if rois.shape != (b, max_boxes, 4) or scores.shape != (b, max_boxes) or count.shape != (b,):
+            raise ValueError("out buffers have the wrong shape")
+    else:
+        rois, scores = ctx.empty((b, max_boxes, 4), torch.int16), ctx.empty((b, max_boxes), torch.float32)
+        count = ctx.empty((b,), torch.int32)
     ctx.call("frcnn_proposals", ptr(regr), ptr(cls), anc, rows, cols, a, int(stride), int(k), float(overlap_thresh),
              max_boxes, b, ptr(rois), ptr(scores), ptr(count))
     return rois, scores, count
@@ -159,7 +172,7 @@ def label_rois(rois, gt, gt_cls, n_gt, n_classes, n_roi=None):
     return out_rois, out_cls, out_bbreg, src, count
 
 
-def roi_forward(feat, rois, pool, mode="resize"):
+def roi_forward(feat, rois, pool, mode="resize", out=None):
     """K-d forward.  feat (B,H,W,C) f32 channels-last, rois (B,N,4) i16/i32/f32 ->
     out (B,N,P,P,C) f32 [, argmax (B,N,P,P,C) i32 in max mode].  custom_layers.py:35-56."""
     feat = _chk(feat, torch.float32, "feat", 4)
@@ -169,7 +182,12 @@ def roi_forward(feat, rois, pool, mode="resize"):
     ctx = get_context(feat.device)
     b, h, w, c = feat.shape
     n, p = rois.shape[1], int(pool)
-    out = ctx.empty((b, n, p, p, c), torch.float32)
+    if out is not None:
+        out = _chk_out(out, torch.float32, "out", 5)
+        if out.shape != (b, n, p, p, c):
+            raise ValueError("out buffer has the wrong shape")
+    else:
+        out = ctx.empty((b, n, p, p, c), torch.float32)
     argmax = ctx.empty((b, n, p, p, c), torch.int32) if mode == "max" else None
     ctx.call("frcnn_roi_fwd", _MODES[mode], ptr(feat), h, w, c, ptr(rois), _ROI_DTYPES[rois.dtype], n, p, b,
              ptr(out), ptr(argmax))
@@ -254,7 +272,7 @@ def valid_boxes(boxes):
     return index, count
 
 
-def pad_rois(rois, count, group=64):
+def pad_rois(rois, count, group=64, out=None):
     """voc_dets.py:37-46 on the device: rois (B,n_max,4) i16 + count (B,) -> padded (B,M,4) i16 with
     M = n_max rounded up to `group` (last detector batch filled with copies of its first RoI, unused
     rows = empty box) and rows (B,) i32 = count rounded up."""
@@ -262,6 +280,11 @@ def pad_rois(rois, count, group=64):
     ctx = get_context(rois.device)
     b, n_max, _ = rois.shape
     m = -(-n_max // group) * group
-    out, rows = ctx.empty((b, m, 4), torch.int16), ctx.empty((b,), torch.int32)
+    if out is not None:
+        out, rows = _chk_out(out[0], torch.int16, "out rois", 3), _chk_out(out[1], torch.int32, "out rows", 1)
+        if out.shape != (b, m, 4) or rows.shape != (b,):
+            raise ValueError("out buffers have the wrong shape")
+    else:
+        out, rows = ctx.empty((b, m, 4), torch.int16), ctx.empty((b,), torch.int32)
     ctx.call("frcnn_pad_rois", ptr(rois), ptr(count), n_max, int(group), m, b, ptr(out), ptr(rows))
     return out, rows

@@ -22,32 +22,17 @@ from .shared_constants import DEFAULT_ANCHORS
 
 class ProposalRoiPipeline:
     def __init__(self, anchor_dims=DEFAULT_ANCHORS, stride=16, pre_nms_topk=8000, nms_thresh=0.7, max_boxes=300,
-                 num_rois=64, pool_size=7, mode="resize", device=None):
+                 num_rois=64, pool_size=7, mode="resize", device=None, h2d_chunk=8):
         self.anchor_dims = np.asarray(anchor_dims)
         self.stride, self.k, self.thresh, self.max_boxes = stride, pre_nms_topk, nms_thresh, max_boxes
         self.num_rois, self.pool_size, self.mode = num_rois, pool_size, mode
         self.ctx = get_context(device)
+        self.h2d_chunk = h2d_chunk
+        self._copy_stream = None
         self._dev = {}
         self._host = {}
 
     # -- staging ----------------------------------------------------------------------------------
-    def _stage_in(self, name, x):
-        """host array -> persistent device buffer (async copy from pinned memory); device tensors pass."""
-        if isinstance(x, torch.Tensor) and x.is_cuda:
-            return x
-        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if not isinstance(x, torch.Tensor) else x
-        buf = self._dev.get(name)
-        if buf is None or buf.shape != t.shape:
-            buf = self._dev[name] = torch.empty(t.shape, dtype=torch.float32, device=self.ctx.device)
-        if not t.is_pinned():
-            pin = self._host.get(name)
-            if pin is None or pin.shape != t.shape:
-                pin = self._host[name] = torch.empty(t.shape, dtype=torch.float32).pin_memory()
-            pin.copy_(t)
-            t = pin
-        buf.copy_(t, non_blocking=True)
-        return buf
-
     def _stage_out(self, name, t):
         pin = self._host.get(name)
         if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
@@ -73,15 +58,75 @@ class ProposalRoiPipeline:
         which stay on the device for the detector head exactly like the RoI layer's output inside the
         reference's TF graph.  `on_device(rois, scores, count)` (optional) is invoked with the device
         tensors before the read-back, e.g. to enqueue the multi-GPU all-gather of the final RoIs.
-        One stream synchronisation at the end."""
-        cls_d, regr_d, feat_d = self._stage_in("cls", cls), self._stage_in("regr", regr), self._stage_in("feat", feat)
-        rois, scores, count, padded, pooled = self.run_device(cls_d, regr_d, feat_d)
+
+        Host inputs are uploaded in chunks of `h2d_chunk` images on a copy stream while the kernels of
+        the previous chunk run (images are independent, so chunking does not change any result); one
+        stream synchronisation at the end."""
+        host_in = not (isinstance(cls, torch.Tensor) and cls.is_cuda)
+        if not host_in:
+            rois, scores, count, padded, pooled = self.run_device(cls, regr, feat)
+        else:
+            rois, scores, count, padded, pooled = self._run_chunked(cls, regr, feat)
         if on_device is not None:
             on_device(rois, scores, count)
         h_rois, h_scores, h_count = (self._stage_out("rois", rois), self._stage_out("scores", scores),
                                      self._stage_out("count", count))
         torch.cuda.current_stream(self.ctx.device).synchronize()
         return h_rois.numpy(), h_scores.numpy(), h_count.numpy(), pooled
+
+    def _pinned(self, name, x):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(torch.float32).contiguous()
+        if t.is_pinned():
+            return t
+        pin = self._host.get(name)
+        if pin is None or pin.shape != t.shape:
+            pin = self._host[name] = torch.empty(t.shape, dtype=torch.float32).pin_memory()
+        pin.copy_(t)
+        return pin
+
+    def _device_buffer(self, name, shape, dtype):
+        buf = self._dev.get(name)
+        if buf is None or buf.shape != torch.Size(shape) or buf.dtype != dtype:
+            buf = self._dev[name] = torch.empty(shape, dtype=dtype, device=self.ctx.device)
+        return buf
+
+    def _run_chunked(self, cls, regr, feat):
+        dev = self.ctx.device
+        srcs = {"cls": self._pinned("cls", cls), "regr": self._pinned("regr", regr), "feat": self._pinned("feat", feat)}
+        b = srcs["cls"].shape[0]
+        bufs = {k: self._device_buffer(k, v.shape, torch.float32) for k, v in srcs.items()}
+        m = -(-self.max_boxes // self.num_rois) * self.num_rois
+        rois = self._device_buffer("o_rois", (b, self.max_boxes, 4), torch.int16)
+        scores = self._device_buffer("o_scores", (b, self.max_boxes), torch.float32)
+        count = self._device_buffer("o_count", (b,), torch.int32)
+        padded = self._device_buffer("o_padded", (b, m, 4), torch.int16)
+        rows = self._device_buffer("o_rows", (b,), torch.int32)
+        pooled = torch.empty((b, m, self.pool_size, self.pool_size, feat.shape[3]), dtype=torch.float32, device=dev)
+        if self.mode != "resize":
+            raise NotImplementedError("host-staged calls support mode='resize'; use run_device for max mode")
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._copy_stream.wait_stream(cur)            # the previous call's kernels no longer read the buffers
+        events = []
+        step = max(1, int(self.h2d_chunk))
+        with torch.cuda.stream(self._copy_stream):
+            for lo in range(0, b, step):
+                hi = min(b, lo + step)
+                for k in ("cls", "regr", "feat"):
+                    bufs[k][lo:hi].copy_(srcs[k][lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append((lo, hi, ev))
+        for lo, hi, ev in events:
+            cur.wait_event(ev)
+            ops.proposals(bufs["regr"][lo:hi], bufs["cls"][lo:hi], self.anchor_dims, self.stride, self.k, self.thresh,
+                          self.max_boxes, out=(rois[lo:hi], scores[lo:hi], count[lo:hi]))
+            ops.pad_rois(rois[lo:hi], count[lo:hi], self.num_rois, out=(padded[lo:hi], rows[lo:hi]))
+            ops.roi_forward(bufs["feat"][lo:hi], padded[lo:hi], self.pool_size, self.mode, out=pooled[lo:hi])
+        return rois, scores, count, padded, pooled
 
     @staticmethod
     def h2d_bytes(cls, regr, feat):

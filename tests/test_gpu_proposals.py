@@ -289,3 +289,26 @@ def test_dropin_det_util_functions():
     wb, wp, _ = O.topk_proposals(dense.copy(), cls.reshape(-1), 8000)
     pick = O.greedy_nms(wb, wp, 0.7, 300)
     assert mgr.conv_only and conv.shape == (1, 38, 63, 8) and rois.dtype == np.int16 and np.array_equal(rois, wb[pick])
+
+
+def test_pipeline_host_staged_equals_device_path(ops):
+    """ProposalRoiPipeline.__call__ (pinned host inputs, chunked upload overlapping compute) must equal the
+    device-resident path and the per-stage ops, for batch sizes that are not a multiple of the chunk."""
+    import torch
+    from faster_rcnn_b200 import synth
+    from faster_rcnn_b200.pipeline import ProposalRoiPipeline
+    dims = O.anchor_table([128, 256, 512])
+    b = 5
+    pairs = [synth.rpn_outputs(19, 25, 9, 40 + i, clustered=bool(i % 2)) for i in range(b)]
+    cls, regr = np.concatenate([p[0] for p in pairs]), np.concatenate([p[1] for p in pairs])
+    feat = np.concatenate([synth.feature_map(19, 25, 32, 50 + i) for i in range(b)])
+    pipe = ProposalRoiPipeline(dims, 16, 2000, 0.7, 300, 64, 7, h2d_chunk=2)
+    rois, scores, count, pooled = pipe(cls, regr, feat)
+    d_rois, d_scores, d_count, d_padded, d_pooled = pipe.run_device(dev(cls), dev(regr), dev(feat))
+    assert np.array_equal(rois, host(d_rois)) and np.array_equal(scores, host(d_scores)) and np.array_equal(count, host(d_count))
+    assert torch.equal(pooled, d_pooled)
+    again = pipe(cls, regr, feat)                      # buffers are reused across calls
+    assert np.array_equal(again[0], rois) and torch.equal(again[3], d_pooled)
+    from oracle import roi_oracle as R
+    n0 = int(count[0])
+    assert np.array_equal(host(pooled)[0, :n0], R.roi_resize_fwd(feat[0], rois[0, :n0], 7))
