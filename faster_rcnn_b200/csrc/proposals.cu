@@ -3,10 +3,10 @@
 // Kernel 1 (decode_kernel): one thread per anchor, fully parallel over (anchor, image).
 //   Reads regr (16 B) + cls (4 B), writes one 64-bit sort key and one packed int16x4 box
 //   (16 B) per anchor.  HBM-bound, coalesced 128-bit loads/stores.
-// Kernel 2 (topk_kernel): one CTA per image.  MSB-first 8-bit radix select over the
+// Kernel 2 (topk_kernel): one CTA per image.  MSB-first 11-bit radix select over the
 //   64-bit keys (unique because the anchor index is part of the key) finds the exact
-//   k-th largest key, survivors are compacted into shared memory, bitonic-sorted
-//   descending and gathered into the output arrays.
+//   k-th largest key, survivors are compacted into shared memory, sorted descending with a
+//   register-blocked bitonic network and gathered into the output arrays.
 //
 // Reference semantics (file:line under /root/reference/faster_rcnn):
 //   det_util.py:162-175 anchors (centre = cell index, x1 = x - w//2, x2 = x1 + w)
@@ -23,146 +23,283 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ r
                                                      int rows, int cols, int n_per_image,
                                                      unsigned long long* __restrict__ keys,
                                                      BoxI16* __restrict__ boxes,
-                                                     float4* __restrict__ dense) {
+                                                     float4* __restrict__ dense,
+                                                     int* __restrict__ valid_count) {
   const int img = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_per_image) return;
-  const size_t g = (size_t)img * n_per_image + i;
-  const int a = i % tab.n;
-  const int loc = i / tab.n;
-  const int cx_i = loc % cols, cy_i = loc / cols;
-  const int aw = tab.w[a], ah = tab.h[a];
+  bool valid = false;
+  if (i < n_per_image) {
+    const size_t g = (size_t)img * n_per_image + i;
+    const int a = i % tab.n;
+    const int loc = i / tab.n;
+    const int cx_i = loc % cols, cy_i = loc / cols;
+    const int aw = tab.w[a], ah = tab.h[a];
 
-  // anchors are integer valued -> exact in float32
-  float x = (float)(cx_i - (aw >> 1));
-  float y = (float)(cy_i - (ah >> 1));
-  float w = (float)aw;     // (x + aw) - x
-  float hgt = (float)ah;
+    // anchors are integer valued -> exact in float32
+    float x = (float)(cx_i - (aw >> 1));
+    float y = (float)(cy_i - (ah >> 1));
+    float w = (float)aw;     // (x + aw) - x
+    float hgt = (float)ah;
 
-  const float4 r = ldg_f4(regr + 4 * g);
-  const float tx = __fdiv_rn(r.x, 10.0f), ty = __fdiv_rn(r.y, 10.0f);
-  const float tw = __fdiv_rn(r.z, 5.0f), th = __fdiv_rn(r.w, 5.0f);
+    const float4 r = ldg_f4(regr + 4 * g);
+    const float tx = __fdiv_rn(r.x, 10.0f), ty = __fdiv_rn(r.y, 10.0f);
+    const float tw = __fdiv_rn(r.z, 5.0f), th = __fdiv_rn(r.w, 5.0f);
 
-  x = __fadd_rn(x, __fdiv_rn(w, 2.0f));
-  y = __fadd_rn(y, __fdiv_rn(hgt, 2.0f));
-  x = __fadd_rn(x, __fmul_rn(tx, w));
-  y = __fadd_rn(y, __fmul_rn(ty, hgt));
-  w = __fmul_rn(w, expf(tw));
-  hgt = __fmul_rn(hgt, expf(th));
-  x = __fsub_rn(x, __fdiv_rn(w, 2.0f));
-  y = __fsub_rn(y, __fdiv_rn(hgt, 2.0f));
-  x = rintf(x); y = rintf(y); w = rintf(w); hgt = rintf(hgt);     // np.round: half to even
-  float x2 = __fadd_rn(w, x), y2 = __fadd_rn(hgt, y);
+    x = __fadd_rn(x, __fdiv_rn(w, 2.0f));
+    y = __fadd_rn(y, __fdiv_rn(hgt, 2.0f));
+    x = __fadd_rn(x, __fmul_rn(tx, w));
+    y = __fadd_rn(y, __fmul_rn(ty, hgt));
+    w = __fmul_rn(w, expf(tw));
+    hgt = __fmul_rn(hgt, expf(th));
+    x = __fsub_rn(x, __fdiv_rn(w, 2.0f));
+    y = __fsub_rn(y, __fdiv_rn(hgt, 2.0f));
+    x = rintf(x); y = rintf(y); w = rintf(w); hgt = rintf(hgt);     // np.round: half to even
+    float x2 = __fadd_rn(w, x), y2 = __fadd_rn(hgt, y);
 
-  x2 = np_max(__fadd_rn(x, 1.0f), x2);
-  y2 = np_max(__fadd_rn(y, 1.0f), y2);
-  x = np_max(0.0f, x);
-  y = np_max(0.0f, y);
-  x2 = np_min((float)(cols - 1), x2);
-  y2 = np_min((float)(rows - 1), y2);
+    x2 = np_max(__fadd_rn(x, 1.0f), x2);
+    y2 = np_max(__fadd_rn(y, 1.0f), y2);
+    x = np_max(0.0f, x);
+    y = np_max(0.0f, y);
+    x2 = np_min((float)(cols - 1), x2);
+    y2 = np_min((float)(rows - 1), y2);
 
-  if (dense) dense[g] = make_float4(x, y, x2, y2);
+    if (dense) dense[g] = make_float4(x, y, x2, y2);
 
-  const bool valid = (x2 > x) && (y2 > y);
-  unsigned long long key = 0ull;
-  BoxI16 b = {0, 0, 0, 0};
-  if (valid) {
-    key = ((unsigned long long)mono_key(__ldg(cls + g)) << 32) | (unsigned)i;
-    b.x1 = (short)(int)x; b.y1 = (short)(int)y; b.x2 = (short)(int)x2; b.y2 = (short)(int)y2;
+    valid = (x2 > x) && (y2 > y);
+    unsigned long long key = 0ull;
+    BoxI16 b = {0, 0, 0, 0};
+    if (valid) {
+      key = ((unsigned long long)mono_key(__ldg(cls + g)) << 32) | (unsigned)i;
+      b.x1 = (short)(int)x; b.y1 = (short)(int)y; b.x2 = (short)(int)x2; b.y2 = (short)(int)y2;
+    }
+    keys[g] = key;
+    boxes[g] = b;
   }
-  keys[g] = key;
-  boxes[g] = b;
+  // number of valid anchors of the image (top-k needs it): one atomic per warp
+  const unsigned vb = __ballot_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0 && vb) atomicAdd(valid_count + img, __popc(vb));
 }
 
 constexpr int TOPK_THREADS = 1024;
 constexpr int TOPK_WARPS = TOPK_THREADS / 32;
+constexpr int TOPK_BITS = 11;                       // radix-select digit width
+constexpr int TOPK_BINS = 1 << TOPK_BITS;
 
-// One CTA per image.  Dynamic smem: m_pow2 * 8 bytes of sort buffer.
-__global__ void __launch_bounds__(TOPK_THREADS, 1)
-topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __restrict__ boxes_all,
-            const float* __restrict__ cls_all, int n, int k, int m_pow2,
-            BoxI16* __restrict__ out_boxes, float* __restrict__ out_scores,
-            int* __restrict__ out_index, int* __restrict__ out_count) {
-  extern __shared__ __align__(16) unsigned long long sbuf[];
-  __shared__ unsigned hist[TOPK_WARPS][256];
-  __shared__ unsigned total[256];
-  __shared__ unsigned long long s_prefix;
-  __shared__ int s_need, s_count, s_valid, s_done;
-
-  const int img = blockIdx.x;
-  const unsigned long long* keys = keys_all + (size_t)img * n;
-  const int tid = threadIdx.x, warp = tid >> 5;
-
-  // pass 0: number of valid anchors
-  int local_valid = 0;
-  for (int i = tid; i < n; i += TOPK_THREADS) local_valid += (keys[i] != 0ull);
-  local_valid = __reduce_add_sync(0xffffffffu, local_valid);
-  if (tid == 0) { s_valid = 0; s_count = 0; s_done = 0; }
+// block-wide inclusive scan of one int per thread (1024 threads); `warp_tot` is [TOPK_WARPS] shared
+__device__ __forceinline__ int block_inclusive_scan(int v, int* warp_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += u;
+  }
+  if (lane == 31) warp_tot[warp] = v;
   __syncthreads();
-  if ((tid & 31) == 0 && local_valid) atomicAdd(&s_valid, local_valid);
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += u;
+    }
+    warp_tot[lane] = w;
+  }
   __syncthreads();
-  const int n_valid = s_valid;
-  const int m = min(k, n_valid);
+  const int before = warp ? warp_tot[warp - 1] : 0;
+  __syncthreads();                                   // warp_tot is reused by the next call
+  return v + before;
+}
 
-  unsigned long long thresh = 1ull;   // keep every non-zero key
-  if (n_valid > k) {
-    // MSB-first radix select of the k-th largest key.
-    if (tid == 0) { s_prefix = 0ull; s_need = k; }
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      for (int i = tid; i < TOPK_WARPS * 256; i += TOPK_THREADS) (&hist[0][0])[i] = 0u;
-      __syncthreads();
-      if (s_done) break;
-      const unsigned long long prefix = s_prefix;
-      const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
-      for (int i = tid; i < n; i += TOPK_THREADS) {
-        const unsigned long long key = keys[i];
-        if (key != 0ull && (key & himask) == prefix) atomicAdd(&hist[warp][(key >> shift) & 255u], 1u);
+// shared-memory slot of logical element e: one pad entry per E elements keeps the blocked
+// register <-> shared transfers (thread t owns e = t*E .. t*E+E-1) at the 2-way minimum of 64-bit accesses
+template <int E>
+__device__ __forceinline__ int pad_slot(int e) { return e + e / E; }
+
+// Block-wide exact selection: returns a splitter T such that exactly `rank` keys are >= T (keys are
+// unique and non-zero; the caller guarantees 0 < rank < number of valid keys).  MSB-first radix
+// select, 11-bit digits, one shared histogram fed by warp-aggregated atomics (__match_any_sync: one
+// atomic per distinct digit per warp), suffix scan over the bins.  The pass at which the splitter's
+// bucket holds exactly the keys still needed ends it (3 passes for tie-free float scores).
+// Keys are fetched 8 per thread before any is consumed, which hides the L2 latency.
+constexpr int TOPK_U = 8;
+__device__ unsigned long long radix_select(const unsigned long long* __restrict__ keys, int n, int rank,
+                                           unsigned* hist, int* warp_tot, unsigned long long* s_prefix,
+                                           int* s_need, int* s_done) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) { *s_prefix = 0ull; *s_need = rank; *s_done = 0; }
+  __syncthreads();
+  for (int hi = 64; hi > 0;) {
+    const int bits = hi < TOPK_BITS ? hi : TOPK_BITS;
+    const int shift = hi - bits;
+    for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = *s_prefix;
+    const int need = *s_need;
+    for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
+      unsigned long long kk[TOPK_U];
+#pragma unroll
+      for (int u = 0; u < TOPK_U; ++u) {
+        const int i = base + u * TOPK_THREADS + tid;
+        kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
       }
-      __syncthreads();
-      if (tid < 256) {
-        unsigned s = 0;
-        for (int wv = 0; wv < TOPK_WARPS; ++wv) s += hist[wv][tid];
-        total[tid] = s;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int need = s_need;
-        int d = 255;
-        for (; d > 0; --d) {
-          if ((int)total[d] >= need) break;
-          need -= total[d];
+#pragma unroll
+      for (int u = 0; u < TOPK_U; ++u) {
+        const unsigned long long key = kk[u];
+        const bool in = key != 0ull && (hi == 64 || (key >> hi) == (prefix >> hi));
+        const unsigned digit = in ? (unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u)) : 0xffffffffu;
+        if (hi == 64) {
+          // first pass: a handful of distinct digits per warp (sign + exponent bits) -> aggregate
+          const unsigned peers = __match_any_sync(0xffffffffu, digit);
+          if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+        } else if (in) {
+          atomicAdd(&hist[digit], 1u);              // later passes: few keys left and their digits are spread out
         }
-        s_prefix = prefix | ((unsigned long long)d << shift);
-        s_need = need;
-        if (shift == 0 || (int)total[d] == need) s_done = 1;   // bucket taken whole: low bits are free
       }
-      __syncthreads();
     }
     __syncthreads();
-    thresh = s_prefix;   // every key >= thresh (in the selected high bits) survives; exactly k of them
+    // suffix scan from the top bin: thread t owns bins BINS-1-2t (c0) and BINS-2-2t (c1)
+    const int c0 = (int)hist[TOPK_BINS - 1 - 2 * tid], c1 = (int)hist[TOPK_BINS - 2 - 2 * tid];
+    const int incl = block_inclusive_scan(c0 + c1, warp_tot);
+    const int excl = incl - c0 - c1;
+    int d = -1, rest = 0, cnt = 0;
+    if (excl < need && excl + c0 >= need) { d = TOPK_BINS - 1 - 2 * tid; rest = need - excl; cnt = c0; }
+    else if (excl + c0 < need && incl >= need) { d = TOPK_BINS - 2 - 2 * tid; rest = need - excl - c0; cnt = c1; }
+    if (d >= 0) {                                   // exactly one thread
+      *s_prefix = prefix | ((unsigned long long)d << shift);
+      *s_need = rest;
+      if (shift == 0 || cnt == rest) *s_done = 1;   // bucket taken whole: the low bits are free
+    }
+    __syncthreads();
+    hi = shift;
+    if (*s_done) break;
+  }
+  const unsigned long long t = *s_prefix;
+  __syncthreads();
+  return t;
+}
+
+// `splits` CTAs per image.  CTA r produces ranks [r*k/splits, (r+1)*k/splits) of the descending top-k
+// order on its own: it selects the two splitters that bound its slice (exact radix select over all
+// keys of the image, L2-resident), compacts the keys between them into shared memory and sorts them
+// with a bitonic network that keeps E keys per thread in registers: strides < E are register swaps,
+// strides < 32E warp shuffles, only strides >= 32E go through shared memory.  The slices need no
+// merge and no inter-CTA communication, and the n log^2 n sort work shrinks with the slice.
+template <int E>
+__global__ void __launch_bounds__(TOPK_THREADS, 1)
+topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __restrict__ boxes_all,
+            const float* __restrict__ cls_all, const int* __restrict__ valid_count, int n, int k, int splits,
+            BoxI16* __restrict__ out_boxes, float* __restrict__ out_scores, int* __restrict__ out_index,
+            int* __restrict__ out_count) {
+  constexpr int M = TOPK_THREADS * E;                 // sort size (power of two), >= slice length
+  extern __shared__ __align__(16) unsigned long long sbuf[];      // pad_slot<E>(M) entries
+  __shared__ unsigned hist[TOPK_BINS];
+  __shared__ int warp_tot[TOPK_WARPS];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_need, s_count, s_done;
+
+  const int img = blockIdx.x / splits, part = blockIdx.x - img * splits;
+  const unsigned long long* keys = keys_all + (size_t)img * n;
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  const int n_valid = __ldg(valid_count + img);       // counted by decode_kernel
+  const int m = min(k, n_valid);
+  const int first = (int)((long long)part * k / splits);                       // ranks [first, last) belong to this CTA
+  const int slice_end = (int)((long long)(part + 1) * k / splits);
+  const int last = min(slice_end, m);
+
+  // splitters: keys >= t_lo and < t_hi are exactly the ranks [first, last)
+  unsigned long long t_hi = ~0ull, t_lo = 1ull;
+  if (first < last) {
+    if (first > 0) t_hi = radix_select(keys, n, first, hist, warp_tot, &s_prefix, &s_need, &s_done);
+    if (last < n_valid) t_lo = radix_select(keys, n, last, hist, warp_tot, &s_prefix, &s_need, &s_done);
   }
 
-  // compaction of survivors into shared memory (order irrelevant, sorted next)
-  for (int base = 0; base < n; base += TOPK_THREADS) {
-    const int i = base + tid;
-    const unsigned long long key = (i < n) ? keys[i] : 0ull;
-    const bool take = key != 0ull && key >= thresh;
-    const unsigned ballot = __ballot_sync(0xffffffffu, take);
-    int wbase = 0;
-    if ((tid & 31) == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (take) sbuf[wbase + __popc(ballot & ((1u << (tid & 31)) - 1u))] = key;
+  // compaction of the slice into shared memory (order irrelevant, sorted next)
+  if (first < last) {
+    for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
+      unsigned long long kk[TOPK_U];
+#pragma unroll
+      for (int u = 0; u < TOPK_U; ++u) {
+        const int i = base + u * TOPK_THREADS + tid;
+        kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < TOPK_U; ++u) {
+        const bool take = kk[u] != 0ull && kk[u] >= t_lo && (first == 0 || kk[u] < t_hi);
+        const unsigned ballot = __ballot_sync(0xffffffffu, take);
+        int wbase = 0;
+        if (lane == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (take) sbuf[pad_slot<E>(wbase + __popc(ballot & ((1u << lane) - 1u)))] = kk[u];
+      }
+    }
   }
   __syncthreads();
-  for (int i = s_count + tid; i < m_pow2; i += TOPK_THREADS) sbuf[i] = 0ull;   // pad with the smallest key
-  bitonic_sort_desc(sbuf, m_pow2);
+  for (int i = s_count + tid; i < M; i += TOPK_THREADS) sbuf[pad_slot<E>(i)] = 0ull;   // pad with the smallest key
+  __syncthreads();
+
+  // ---- bitonic sort, descending, E keys per thread in registers ----
+  unsigned long long v[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) v[i] = sbuf[pad_slot<E>(tid * E + i)];
+  for (int size = 2; size <= M; size <<= 1) {
+    int stride = size >> 1;
+    if (stride >= 32 * E) {
+      // cross-warp strides of this merge level: classic shared-memory passes
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < E; ++i) sbuf[pad_slot<E>(tid * E + i)] = v[i];
+      for (; stride >= 32 * E; stride >>= 1) {
+        __syncthreads();
+        for (int t = tid; t < (M >> 1); t += TOPK_THREADS) {
+          const int lo = 2 * t - (t & (stride - 1)), hi2 = lo + stride;
+          const bool desc = ((lo & size) == 0);
+          const unsigned long long a = sbuf[pad_slot<E>(lo)], b = sbuf[pad_slot<E>(hi2)];
+          if ((a < b) == desc) { sbuf[pad_slot<E>(lo)] = b; sbuf[pad_slot<E>(hi2)] = a; }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < E; ++i) v[i] = sbuf[pad_slot<E>(tid * E + i)];
+    }
+    for (; stride >= E; stride >>= 1) {              // partner in another lane of the warp
+      const int lane_xor = stride / E;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[i], lane_xor);
+        const int e = tid * E + i;
+        const bool want_max = ((e & stride) == 0) == ((e & size) == 0);
+        v[i] = want_max ? (v[i] > other ? v[i] : other) : (v[i] < other ? v[i] : other);
+      }
+    }
+#pragma unroll
+    for (int st = E >> 1; st > 0; st >>= 1) {        // partner in the same thread
+      if (st <= stride) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+          if ((i & st) == 0) {
+            const int e = tid * E + i;
+            const bool desc = ((e & size) == 0);
+            const unsigned long long a = v[i], b = v[i | st];
+            if ((a < b) == desc) { v[i] = b; v[i | st] = a; }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < E; ++i) sbuf[pad_slot<E>(tid * E + i)] = v[i];
+  __syncthreads();
 
   const BoxI16* boxes = boxes_all + (size_t)img * n;
   const float* cls = cls_all + (size_t)img * n;
-  for (int r = tid; r < k; r += TOPK_THREADS) {
+  for (int r = first + tid; r < slice_end; r += TOPK_THREADS) {
     const size_t o = (size_t)img * k + r;
-    if (r < m) {
-      const int idx = (int)(unsigned)(sbuf[r] & 0xffffffffull);
+    if (r < last) {
+      const int idx = (int)(unsigned)(sbuf[pad_slot<E>(r - first)] & 0xffffffffull);
       out_boxes[o] = boxes[idx];
       out_scores[o] = __ldg(cls + idx);
       out_index[o] = idx;
@@ -172,7 +309,21 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
       out_index[o] = -1;
     }
   }
-  if (tid == 0) out_count[img] = m;
+  if (tid == 0 && part == 0) out_count[img] = m;
+}
+
+template <int E>
+static int launch_topk(frcnn_handle* h, cudaStream_t stream, const unsigned long long* keys, const BoxI16* boxes,
+                       const float* cls, const int* valid_count, int n, int k, int splits, int batch, BoxI16* out_boxes,
+                       float* out_scores, int32_t* out_index, int32_t* out_count) {
+  const size_t smem = (size_t)(TOPK_THREADS * E + TOPK_THREADS) * sizeof(unsigned long long);
+  if (smem + 12 * 1024 > (size_t)h->max_smem_optin)
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k too large for the shared-memory sort%s%s");
+  FRCNN_CUDA(h, cudaFuncSetAttribute(topk_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_kernel<E><<<batch * splits, TOPK_THREADS, smem, stream>>>(keys, boxes, cls, valid_count, n, k, splits, out_boxes,
+                                                               out_scores, out_index, out_count);
+  FRCNN_LAUNCH_CHECK(h, "topk_kernel");
+  return FRCNN_OK;
 }
 
 int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, const float* cls,
@@ -180,30 +331,32 @@ int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, 
                        int16_t* out_boxes, float* out_scores, int32_t* out_index,
                        int32_t* out_count, float* dense_boxes) {
   const int n = rows * cols * tab.n;
-  int m_pow2 = 1;
-  while (m_pow2 < k) m_pow2 <<= 1;
-  if (m_pow2 > n) { int p = 1; while (p < n) p <<= 1; m_pow2 = p < m_pow2 ? p : m_pow2; }
-  const size_t smem = (size_t)m_pow2 * sizeof(unsigned long long);
-  if (smem + 40 * 1024 > (size_t)h->max_smem_optin)
-    return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k too large for the shared-memory sort%s%s");
+  if (k > TOPK_THREADS * 16)
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k above 16384 is not supported%s%s");
   const size_t key_bytes = align_up((size_t)batch * n * sizeof(unsigned long long), 256);
   const size_t box_bytes = align_up((size_t)batch * n * sizeof(BoxI16), 256);
   void* ws = nullptr;
-  int rc = arena_get(h, stream, key_bytes + box_bytes, &ws);
+  int rc = arena_get(h, stream, key_bytes + box_bytes + (size_t)batch * sizeof(int), &ws);
   if (rc) return rc;
   auto* keys = reinterpret_cast<unsigned long long*>(ws);
   auto* boxes = reinterpret_cast<BoxI16*>(reinterpret_cast<char*>(ws) + key_bytes);
+  int* valid_count = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + key_bytes + box_bytes);
+  FRCNN_CUDA(h, cudaMemsetAsync(valid_count, 0, (size_t)batch * sizeof(int), stream));
 
   dim3 grid((n + 255) / 256, batch);
   decode_kernel<<<grid, 256, 0, stream>>>(regr, cls, tab, rows, cols, n, keys, boxes,
-                                         reinterpret_cast<float4*>(dense_boxes));
+                                         reinterpret_cast<float4*>(dense_boxes), valid_count);
   FRCNN_LAUNCH_CHECK(h, "decode_kernel");
-  FRCNN_CUDA(h, cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_kernel<<<batch, TOPK_THREADS, smem, stream>>>(keys, boxes, cls, n, k, m_pow2,
-                                                     reinterpret_cast<BoxI16*>(out_boxes), out_scores,
-                                                     out_index, out_count);
-  FRCNN_LAUNCH_CHECK(h, "topk_kernel");
-  return FRCNN_OK;
+  // CTAs per image: as many rank slices as keep the GPU filled in one wave, slices of >= 1024 keys
+  int splits = 1;
+  while (splits < 8 && (long long)batch * splits * 2 <= h->sm_count && k / (splits * 2) >= 1024) splits <<= 1;
+  const int slice = (k + splits - 1) / splits + 1;
+  auto* ob = reinterpret_cast<BoxI16*>(out_boxes);
+  if (slice <= TOPK_THREADS * 1) return launch_topk<1>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
+  if (slice <= TOPK_THREADS * 2) return launch_topk<2>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
+  if (slice <= TOPK_THREADS * 4) return launch_topk<4>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
+  if (slice <= TOPK_THREADS * 8) return launch_topk<8>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
+  return launch_topk<16>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
 }
 
 }  // namespace frcnn
