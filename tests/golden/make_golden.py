@@ -67,8 +67,33 @@ def labels_case(ref, tag, img, dims, conv_dims):
          y_class=y_class, y_bbreg=y_bbreg, py_random_seed=1)
 
 
+def voc_gt_case(ref, n_images=200):
+    """Real ground truth: the first `n_images` VOC2007 trainval annotations the reference ships
+    (test_data/VOC_test, XML only), resized like training (600/1000), with a digest of the reference's labels."""
+    import hashlib
+    root = '/root/reference/test_data/VOC_test'
+    names = [l.strip() for l in open(root + '/ImageSets/Main/trainval.txt')][:n_images]
+    dims = ref.util.get_anchors([128, 256, 512])
+    rows, offs, whs, digests, npos, nuse = [], [0], [], [], [], []
+    for nm in names:
+        img = ref.voc.extract_img_data(root, nm).resize_within_bounds(600, 1000)[0]
+        rows.append(ref.util.get_bbox_coords(img.gt_boxes))
+        offs.append(offs[-1] + len(rows[-1]))
+        whs.append([img.width, img.height])
+        mgr = ref.rpn_util.RpnTrainingManager(O.conv_dims_resnet, 16, preprocess_func=None, anchor_dims=dims)
+        with ref_loader.quiet():
+            mgr._process(img)
+        c = mgr._cache[img.cache_key]
+        digests.append(hashlib.sha1(c['can_use'].tobytes() + c['is_pos'].tobytes()).hexdigest()[:16])
+        npos.append(int(c['is_pos'].sum()))
+        nuse.append(int(c['can_use'].sum()))
+    save("voc_gt_200", gt=np.concatenate(rows).astype(np.float32), offsets=np.array(offs), img_wh=np.array(whs),
+         names=np.array(names), label_sha1=np.array(digests), n_pos=np.array(npos), n_use=np.array(nuse))
+
+
 def main():
     ref = ref_loader.load()
+    voc_gt_case(ref)
     # P1: anchor tables
     save("anchors", voc=ref.util.get_anchors([128, 256, 512]), default=ref.shared_constants.DEFAULT_ANCHORS,
          scales_voc=np.array([128, 256, 512]))

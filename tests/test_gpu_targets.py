@@ -68,6 +68,28 @@ def test_label_anchors_batch_vs_oracle(ops, rows_cols, wh, scales, n_gts):
         assert counts[b].tolist() == [int((wcu & wip).sum()), int((wcu & ~wip).sum())]
 
 
+def test_label_anchors_on_real_voc_ground_truth(ops):
+    """200 real VOC2007 annotation sets: labels must hash to the digests recorded from the reference;
+    images of equal conv shape go through the kernel as one batch."""
+    import hashlib
+    g = golden("voc_gt_200")
+    dims = O.anchor_table([128, 256, 512])
+    groups = {}
+    for i in range(len(g["names"])):
+        w, h = (int(v) for v in g["img_wh"][i])
+        groups.setdefault(tuple(O.conv_dims_resnet(h, w)), []).append(i)
+    checked = 0
+    for (rows, cols), idxs in groups.items():
+        gts = [g["gt"][g["offsets"][i]:g["offsets"][i + 1]] for i in idxs]
+        cu, ip, bb, counts = _label(ops, gts, [g["img_wh"][i] for i in idxs], rows, cols, dims)
+        for b, i in enumerate(idxs):
+            cub, ipb = cu[b].view(np.bool_), ip[b].view(np.bool_)
+            assert hashlib.sha1(cub.tobytes() + ipb.tobytes()).hexdigest()[:16] == str(g["label_sha1"][i]), g["names"][i]
+            assert int(ipb.sum()) == int(g["n_pos"][i]) and int(cub.sum()) == int(g["n_use"][i])
+            checked += 1
+    assert checked == 200
+
+
 def test_label_anchors_degenerate_gt(ops):
     """GT outside every anchor (max IoU 0 -> no forced positive), duplicated GTs (shared arg-max anchor)."""
     dims = O.anchor_table([128, 256, 512])

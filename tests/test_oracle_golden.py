@@ -86,3 +86,17 @@ def test_nms_f64_and_iou():
     assert np.array_equal(O.iou_matrix(g["rois_i16"], g["gt_feat"]), g["iou_i16"])
     assert np.array_equal(O.pixel_anchors(6, 9, O.anchor_table([128, 256, 512]), 16), g["anchors"])
     assert O.nms(g["boxes"][:0], g["probs"][:0]) == []
+
+
+def test_labels_on_real_voc_ground_truth():
+    """200 real VOC2007 annotation sets (SURVEY 8c iv): the oracle's labels hash to the reference's."""
+    import hashlib
+    g = golden("voc_gt_200")
+    dims = O.anchor_table([128, 256, 512])
+    for i in range(0, len(g["names"]), 4):                       # every 4th image keeps the CPU suite fast
+        w, h = (int(v) for v in g["img_wh"][i])
+        gt = g["gt"][g["offsets"][i]:g["offsets"][i + 1]]
+        rows, cols = O.conv_dims_resnet(h, w)
+        cu, ip, _ = O.label_anchors(w, h, gt, rows, cols, dims, 16)
+        assert hashlib.sha1(cu.tobytes() + ip.tobytes()).hexdigest()[:16] == str(g["label_sha1"][i])
+        assert int(ip.sum()) == int(g["n_pos"][i]) and int(cu.sum()) == int(g["n_use"][i])

@@ -44,6 +44,11 @@ def _worker(rank, world, port, n_images, out_dir):
     start, stop = parallel.shard_range(n_images, r, w)
     dets, counts = parallel.pack_detections(*_dets_for(range(start, stop)))
     all_d, all_c = parallel.all_gather_detections(dets, counts)
+    # the proposal stage's exchange: int16 RoI rows travel as int32 views
+    rois = (torch.arange((stop - start) * 5 * 4, dtype=torch.int32).reshape(stop - start, 5, 4) + 1000 * rank).to(torch.int16)
+    g_rois, g_cnt = parallel.all_gather_rois(rois, torch.full((stop - start,), rank, dtype=torch.int32))
+    assert g_rois.dtype == torch.int16 and g_rois.shape == (n_images, 5, 4)
+    assert torch.equal(g_rois[start:stop], rois) and g_cnt.tolist() == [0] * (n_images // 2) + [1] * (n_images // 2)
     torch.save((all_d, all_c), os.path.join(out_dir, "rank%d.pt" % rank))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
