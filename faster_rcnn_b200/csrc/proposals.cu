@@ -75,9 +75,9 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ r
     keys[g] = key;
     boxes[g] = b;
   }
-  // number of valid anchors of the image (top-k needs it): one atomic per warp
-  const unsigned vb = __ballot_sync(0xffffffffu, valid);
-  if ((threadIdx.x & 31) == 0 && vb) atomicAdd(valid_count + img, __popc(vb));
+  // number of valid anchors of the image (top-k needs it): one atomic per CTA
+  const int nv = __syncthreads_count(valid);
+  if (threadIdx.x == 0 && nv) atomicAdd(valid_count + img, nv);
 }
 
 constexpr int TOPK_THREADS = 1024;
