@@ -127,7 +127,8 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const int4* 
       const float* row_hi = f + (size_t)(ty.x >> 16) * row_stride;
       const float ly = __int_as_float(ty.y);
       float* o = out + obase + (size_t)ph * P * C;
-      // Measured and rejected (profiles/roi_fwd_r01.md): issuing the tap loads of 2/4/7 outputs ahead
+      // Measured and rejected (profiles/README.md): L1-bypassing tap loads (ld.global.nc.L1::no_allocate and
+      // ld.global.cg: 1.10-1.12 ms vs 0.92 ms -- the 34 % L1 hit rate matters), issuing the tap loads of 2/4/7 outputs ahead
       // (no gain: the kernel is bound by L1/TEX + DRAM-write throughput, not load latency) and keeping
       // the last two source columns in registers (fewer loads, but the extra registers cost more
       // occupancy than the loads saved).
@@ -377,19 +378,22 @@ roi_bwd_max_cell_kernel(const float* __restrict__ gout, const int* __restrict__ 
           const int pw = __ffs(mxx) - 1;
           mxx &= mxx - 1;
           const size_t o = (size_t)((roi_row + ph) * P + pw) * C + cbase;
+          // arg-max and dY rows are requested together (no dependent second round trip); a lane whose
+          // channels did not select this cell simply drops its dY values
           int4 a[CPB];
-#pragma unroll
-          for (int j = 0; j < CPB; ++j)
-            a[j] = (cbase + j * 128 < C) ? __ldg(reinterpret_cast<const int4*>(a_img + o + j * 128)) : make_int4(-1, -1, -1, -1);
+          float4 g[CPB];
 #pragma unroll
           for (int j = 0; j < CPB; ++j) {
-            if (a[j].x == cell || a[j].y == cell || a[j].z == cell || a[j].w == cell) {
-              const float4 g = ldg_f4(g_img + o + j * 128);
-              if (a[j].x == cell) acc[j].x += g.x;
-              if (a[j].y == cell) acc[j].y += g.y;
-              if (a[j].z == cell) acc[j].z += g.z;
-              if (a[j].w == cell) acc[j].w += g.w;
-            }
+            const bool live = cbase + j * 128 < C;
+            a[j] = live ? __ldg(reinterpret_cast<const int4*>(a_img + o + j * 128)) : make_int4(-1, -1, -1, -1);
+            g[j] = live ? ldg_f4(g_img + o + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < CPB; ++j) {
+            if (a[j].x == cell) acc[j].x += g[j].x;
+            if (a[j].y == cell) acc[j].y += g[j].y;
+            if (a[j].z == cell) acc[j].z += g[j].z;
+            if (a[j].w == cell) acc[j].w += g[j].w;
           }
         }
       }
