@@ -35,7 +35,7 @@ SIGNATURES = {
     "frcnn_label_rois": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "frcnn_roi_fwd": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p]),
     "frcnn_roi_bwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "frcnn_det_postprocess": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _i, _i, _p, _p, _p, _p]),
+    "frcnn_det_postprocess": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _i, _i, _p, _p, _p, _p]),
     "frcnn_cross_ious": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
     "frcnn_box_transform": (_i, [_p, _p, _p, _p, _i, _i, _i, _i]),
     "frcnn_anchor_grid": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),

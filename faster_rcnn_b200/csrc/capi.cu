@@ -24,7 +24,7 @@ int launch_roi_fwd(frcnn_handle*, cudaStream_t, int, const float*, int, int, int
 int launch_roi_bwd(frcnn_handle*, cudaStream_t, int, const float*, const void*, int, const int32_t*, int, int, int,
                    int, int, int, float*);
 int launch_det_postprocess(frcnn_handle*, cudaStream_t, const int16_t*, const float*, const float*, const double*,
-                           int, int, int, int, double, double, int, int, int32_t*, float*, int32_t*, int32_t*);
+                           const int32_t*, int, int, int, int, double, double, int, int, int32_t*, float*, int32_t*, int32_t*);
 
 int launch_cross_ious(frcnn_handle*, cudaStream_t, const void*, int, int, const float*, int, float*);
 int launch_box_transform(frcnn_handle*, cudaStream_t, float*, const float*, int, int, int, int);
@@ -296,7 +296,7 @@ int frcnn_roi_bwd(frcnn_handle* h, void* stream, int mode, const float* grad_out
 }
 
 int frcnn_det_postprocess(frcnn_handle* h, void* stream, const int16_t* rois, const float* out_cls,
-                          const float* out_reg, const double* resize_ratio, int m_rows, int n_classes,
+                          const float* out_reg, const double* resize_ratio, const int32_t* n_rows, int m_rows, int n_classes,
                           int bg_index, int stride, double det_threshold, double nms_thresh, int max_boxes,
                           int batch, int32_t* det_boxes, float* det_probs, int32_t* det_cls, int32_t* det_count) {
   FRCNN_ENTER(h, stream);
@@ -304,7 +304,7 @@ int frcnn_det_postprocess(frcnn_handle* h, void* stream, const int16_t* rois, co
                 "det_postprocess: null pointer");
   FRCNN_REQUIRE(h, m_rows > 0 && n_classes >= 2 && stride > 0 && max_boxes > 0 && batch > 0,
                 "det_postprocess: bad size");
-  return launch_det_postprocess(h, st, rois, out_cls, out_reg, resize_ratio, m_rows, n_classes, bg_index, stride,
+  return launch_det_postprocess(h, st, rois, out_cls, out_reg, resize_ratio, n_rows, m_rows, n_classes, bg_index, stride,
                                 det_threshold, nms_thresh, max_boxes, batch, det_boxes, det_probs, det_cls,
                                 det_count);
 }

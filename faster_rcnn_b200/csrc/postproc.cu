@@ -19,7 +19,8 @@ struct __align__(8) BoxI16 { short x1, y1, x2, y2; };
 
 __global__ void __launch_bounds__(PP_THREADS)
 det_postprocess_kernel(const BoxI16* __restrict__ rois_all, const float* __restrict__ cls_all,
-                       const float* __restrict__ reg_all, const double* __restrict__ ratio_all, int M, int K,
+                       const float* __restrict__ reg_all, const double* __restrict__ ratio_all,
+                       const int* __restrict__ n_rows_all, int M, int K,
                        int bg, int stride, float det_thr, double nms_thr, int max_boxes,
                        int* __restrict__ det_boxes, float* __restrict__ det_probs, int* __restrict__ det_cls,
                        int* __restrict__ det_count) {
@@ -42,12 +43,14 @@ det_postprocess_kernel(const BoxI16* __restrict__ rois_all, const float* __restr
   const float* ocls = cls_all + (size_t)img * M * K;
   const float* oreg = reg_all + (size_t)img * M * 4 * (K - 1);
   const double ratio = ratio_all[img];
+  const int m_live = n_rows_all ? min(max(n_rows_all[img], 0), M) : M;      // rows the detector really saw
 
   for (int c = tid; c < K; c += PP_THREADS) { s_first[c] = 0x7fffffff; s_cnt[c] = 0; }
   __syncthreads();
 
   // 1+2: class choice and float64 decode
   for (int r = tid; r < M; r += PP_THREADS) {
+    if (r >= m_live) { s_cls[r] = -1; continue; }
     const float* p = ocls + (size_t)r * K;
     int c = 0;
     float conf = p[0];
@@ -168,7 +171,7 @@ det_postprocess_kernel(const BoxI16* __restrict__ rois_all, const float* __restr
 }
 
 int launch_det_postprocess(frcnn_handle* h, cudaStream_t stream, const int16_t* rois, const float* out_cls,
-                           const float* out_reg, const double* ratio, int M, int K, int bg, int stride,
+                           const float* out_reg, const double* ratio, const int32_t* n_rows, int M, int K, int bg, int stride,
                            double det_thr, double nms_thr, int max_boxes, int batch, int32_t* det_boxes,
                            float* det_probs, int32_t* det_cls, int32_t* det_count) {
   if (M > PP_MAX_ROWS || K > PP_MAX_CLASSES)
@@ -176,7 +179,7 @@ int launch_det_postprocess(frcnn_handle* h, cudaStream_t stream, const int16_t* 
   const size_t smem = (size_t)M * (32 + 8 + 4 + 2 + 2 + 2 + 1) + 64;
   FRCNN_CUDA(h, cudaFuncSetAttribute(det_postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   det_postprocess_kernel<<<batch, PP_THREADS, smem, stream>>>(reinterpret_cast<const BoxI16*>(rois), out_cls, out_reg,
-                                                           ratio, M, K, bg, stride, (float)det_thr, nms_thr,
+                                                           ratio, n_rows, M, K, bg, stride, (float)det_thr, nms_thr,
                                                            max_boxes, det_boxes, det_probs, det_cls, det_count);
   FRCNN_LAUNCH_CHECK(h, "det_postprocess_kernel");
   return FRCNN_OK;

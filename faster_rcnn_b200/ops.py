@@ -210,13 +210,15 @@ def roi_backward(grad_out, rois, feat_shape, mode="resize", argmax=None):
 
 
 def det_postprocess(rois, out_cls, out_reg, resize_ratio, bg_index, stride=16, det_threshold=0.0, nms_thresh=0.5,
-                    max_boxes=2000):
+                    max_boxes=2000, n_rows=None):
     """K-e.  rois (B,M,4) i16, out_cls (B,M,K) f32, out_reg (B,M,4(K-1)) f32, resize_ratio (B,) f64 ->
     det_boxes (B,M,4) i32, det_probs (B,M) f32, det_cls (B,M) i32, det_count (B,) i32.
     voc_dets.py:51-86."""
     rois = _chk(rois, torch.int16, "rois", 3)
     out_cls, out_reg = _chk(out_cls, torch.float32, "out_cls", 3), _chk(out_reg, torch.float32, "out_reg", 3)
     resize_ratio = _chk(resize_ratio, torch.float64, "resize_ratio", 1)
+    if n_rows is not None:
+        n_rows = _chk(n_rows, torch.int32, "n_rows", 1)
     ctx = get_context(rois.device)
     b, m, _ = rois.shape
     k = out_cls.shape[2]
@@ -224,7 +226,7 @@ def det_postprocess(rois, out_cls, out_reg, resize_ratio, bg_index, stride=16, d
         raise ValueError("out_reg must be (B, M, 4*(K-1))")
     boxes, probs = ctx.empty((b, m, 4), torch.int32), ctx.empty((b, m), torch.float32)
     cls, count = ctx.empty((b, m), torch.int32), ctx.empty((b,), torch.int32)
-    ctx.call("frcnn_det_postprocess", ptr(rois), ptr(out_cls), ptr(out_reg), ptr(resize_ratio), m, k, int(bg_index),
+    ctx.call("frcnn_det_postprocess", ptr(rois), ptr(out_cls), ptr(out_reg), ptr(resize_ratio), ptr(n_rows), m, k, int(bg_index),
              int(stride), float(det_threshold), float(nms_thresh), int(max_boxes), b, ptr(boxes), ptr(probs),
              ptr(cls), ptr(count))
     return boxes, probs, cls, count

@@ -134,3 +134,45 @@ class ProposalRoiPipeline:
 
     def d2h_bytes(self, batch):
         return batch * (self.max_boxes * 8 + self.max_boxes * 4 + 4)
+
+
+class DetectionPipeline(ProposalRoiPipeline):
+    """Whole inference hot path of `voc_dets.get_dets` (voc_dets.py:20-88) for a BATCH of images, device-resident:
+
+        RPN head outputs -> proposals -> 64-RoI padding -> RoI layer -> detector head (caller's callable)
+                         -> per-class post-processing (arg-max class, float64 decode, NMS 0.5, rescale)
+
+    `detector_head(pooled (B,M,P,P,C) f32, rois (B,M,4) i16) -> (out_cls (B,M,K) f32, out_reg (B,M,4(K-1)) f32)` runs on
+    CUDA tensors (the dense layers are not part of this package).  Rows past the reference's padded length
+    (`ceil(n_rois/64)*64`) are ignored, so results equal per-image `get_dets` calls.  With torch.distributed initialised,
+    `gather=True` all-gathers the fixed-size detection buffers of every rank (the path's only collective)."""
+
+    def __init__(self, detector_head, class_mapping, det_threshold=0.0, det_nms_thresh=0.5, det_max_boxes=2000, **kwargs):
+        super().__init__(**kwargs)
+        self.detector_head = detector_head
+        self.class_mapping = class_mapping
+        self.det_threshold, self.det_nms_thresh, self.det_max_boxes = det_threshold, det_nms_thresh, det_max_boxes
+
+    def detect_device(self, cls, regr, feat, resize_ratios, gather=False):
+        """CUDA tensors in -> (det_boxes (B,M,4) i32, det_probs (B,M) f32, det_cls (B,M) i32, det_count (B,) i32)."""
+        rois, scores, count = ops.proposals(regr, cls, self.anchor_dims, self.stride, self.k, self.thresh, self.max_boxes)
+        padded, rows = ops.pad_rois(rois, count, self.num_rois)
+        pooled = ops.roi_forward(feat, padded, self.pool_size, self.mode)
+        out_cls, out_reg = self.detector_head(pooled if self.mode == "resize" else pooled[0], padded)
+        ratios = resize_ratios if isinstance(resize_ratios, torch.Tensor) else \
+            self.ctx.to_device(np.asarray(resize_ratios, dtype=np.float64))
+        dets = ops.det_postprocess(padded, out_cls.contiguous(), out_reg.contiguous(), ratios, self.class_mapping['bg'],
+                                   self.stride, self.det_threshold, self.det_nms_thresh, self.det_max_boxes, n_rows=rows)
+        if gather:
+            from . import parallel
+            packed, counts = parallel.pack_detections(*dets)
+            return parallel.all_gather_detections(packed, counts)
+        return dets
+
+    def detect(self, cls, regr, feat, resize_ratios):
+        """Host or device arrays in -> per image the reference's list of {'bbox', 'cls_name', 'prob'} dicts."""
+        dev_in = [x if (isinstance(x, torch.Tensor) and x.is_cuda) else self.ctx.to_device(x, np.float32) for x in (cls, regr, feat)]
+        boxes, probs, dcls, count = (self.ctx.to_host(t) for t in self.detect_device(*dev_in, resize_ratios))
+        names = {v: k for k, v in self.class_mapping.items()}
+        return [[{'bbox': boxes[b, i].astype(np.int64), 'cls_name': names[int(dcls[b, i])], 'prob': probs[b, i]}
+                 for i in range(int(count[b]))] for b in range(len(count))]

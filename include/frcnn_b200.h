@@ -184,12 +184,14 @@ FRCNN_API int frcnn_roi_bwd(frcnn_handle* h, void* stream, int mode, const float
  * class, f64 decode (util.transform, util.py:55-74), x stride, per-class f64
  * NMS, rescale + half-even rounding.
  *   rois [batch,M,4] i16, out_cls [batch,M,K] f32, out_reg [batch,M,4(K-1)]
- *   f32, resize_ratio [batch] f64.  det_boxes [batch,M,4] i32, det_probs
+ *   f32, resize_ratio [batch] f64, n_rows [batch] i32 (device, may be NULL = M):
+ *   rows >= n_rows[b] are ignored (fixed-shape batches; frcnn_pad_rois gives the
+ *   count the reference's batching would have run).  det_boxes [batch,M,4] i32, det_probs
  *   [batch,M] f32, det_cls [batch,M] i32, det_count [batch]; order = classes by
  *   first appearance, rows in NMS pick order. */
 FRCNN_API int frcnn_det_postprocess(frcnn_handle* h, void* stream, const int16_t* rois, const float* out_cls,
-                          const float* out_reg, const double* resize_ratio, int m_rows,
-                          int n_classes, int bg_index, int stride, double det_threshold,
+                          const float* out_reg, const double* resize_ratio, const int32_t* n_rows,
+                          int m_rows, int n_classes, int bg_index, int stride, double det_threshold,
                           double nms_thresh, int max_boxes, int batch, int32_t* det_boxes,
                           float* det_probs, int32_t* det_cls, int32_t* det_count);
 

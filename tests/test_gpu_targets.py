@@ -269,6 +269,52 @@ def test_get_dets_dropin():
         assert mapping[d['cls_name']] == wc and d['bbox'].tolist() == wbox.tolist() and d['prob'] == wp
 
 
+def test_detection_pipeline_equals_per_image_get_dets():
+    """DetectionPipeline (batched, device-resident) == voc_dets.get_dets image by image, incl. an image with fewer
+    than 300 proposals whose unused fixed-shape rows must be ignored."""
+    import torch
+    from faster_rcnn_b200 import det_util, synth, voc_dets
+    from faster_rcnn_b200.pipeline import DetectionPipeline
+    dims = O.anchor_table([128, 256, 512])
+    mapping = synth.VOC_CLASS_MAPPING
+    shapes = [(37, 62, False), (37, 62, True), (37, 62, False)]
+    pairs = [synth.rpn_outputs(r, c, 9, 700 + i, clustered=cl) for i, (r, c, cl) in enumerate(shapes)]
+    pairs[2][1][..., 2::4] = 20.0            # image 2: every box blows up to the whole map -> identical boxes,
+    pairs[2][1][..., 3::4] = 20.0            # NMS keeps a handful, most fixed-shape rows are unused
+    cls, regr = np.concatenate([p[0] for p in pairs]), np.concatenate([p[1] for p in pairs])
+    feat = np.concatenate([synth.feature_map(37, 62, 16, 710 + i) for i in range(3)])
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    w_cls = torch.randn((16, 21), generator=gen, device="cuda")
+    w_reg = torch.randn((16, 80), generator=gen, device="cuda")
+
+    def head(pooled, rois):                                  # tiny deterministic stand-in for the dense detector head
+        x = pooled.mean(dim=(2, 3)) + rois.to(torch.float32).sum(dim=2, keepdim=True) * 0.01
+        return torch.softmax(x @ w_cls, dim=2), x @ w_reg
+
+    ratios = [1.6, 1.0, 2.0]
+    pipe = DetectionPipeline(head, mapping, anchor_dims=dims)
+    got = pipe.detect(cls, regr, feat, ratios)
+
+    class Detector:                                          # the same head behind the reference's Keras-style interface
+        def predict(self, x):
+            conv, batch = x
+            pooled = ops_mod.roi_forward(dev(conv), dev(batch), 7)
+            oc, orr = head(pooled, dev(batch))
+            return host(oc), host(orr)
+    from faster_rcnn_b200 import ops as ops_mod
+    n_rois = []
+    for b in range(3):
+        mgr = det_util.DetTrainingManager(FakeRpn(cls[b:b + 1], regr[b:b + 1], conv=feat[b:b + 1]), mapping, lambda d: d,
+                                          anchor_dims=dims)
+        img = FakeImage("i%d" % b, 992, 592, [], data=np.zeros((4, 4, 3), np.float32))
+        want = voc_dets.get_dets(mgr, Detector(), img, ratios[b])
+        n_rois.append(len(mgr.get_det_inputs(img)[1]))
+        assert len(got[b]) == len(want)
+        for d, w in zip(got[b], want):
+            assert d['cls_name'] == w['cls_name'] and d['bbox'].tolist() == w['bbox'].tolist() and d['prob'] == w['prob']
+    assert n_rois[0] == 300 and n_rois[2] < 256, n_rois     # image 2 really exercises the ignored rows
+
+
 # ------------------------------------------------------------------------------------------------
 # stand-alone helpers (util.py surface)
 # ------------------------------------------------------------------------------------------------
