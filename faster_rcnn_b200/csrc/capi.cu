@@ -33,6 +33,11 @@ int launch_valid_boxes(frcnn_handle*, cudaStream_t, const float*, int, int32_t*,
 int launch_pad_rois(frcnn_handle*, cudaStream_t, const int16_t*, const int32_t*, int, int, int, int, int16_t*,
                     int32_t*);
 
+int launch_rpn_losses(frcnn_handle*, cudaStream_t, const uint8_t*, const uint8_t*, const float*, const float*,
+                      const float*, int, int, float*, float*, float*);
+int launch_det_losses(frcnn_handle*, cudaStream_t, const int32_t*, const float*, const float*, const float*, int, int,
+                      int, float*, float*, float*);
+
 // ---- scratch arena -------------------------------------------------------------------------
 // Bump allocator over one device block.  Every public entry point starts with arena_reset();
 // the launchers then carve their workspaces with arena_get().  When a call needs more than the
@@ -355,6 +360,27 @@ int frcnn_pad_rois(frcnn_handle* h, void* stream, const int16_t* rois, const int
   FRCNN_REQUIRE(h, n_max > 0 && group > 0 && batch > 0 && batch <= 65535, "pad_rois: bad size");
   FRCNN_REQUIRE(h, m_out >= (n_max + group - 1) / group * group, "pad_rois: m_out smaller than n_max rounded up to the group size");
   return launch_pad_rois(h, st, rois, count, n_max, group, m_out, batch, out, out_rows);
+}
+
+int frcnn_rpn_losses(frcnn_handle* h, void* stream, const uint8_t* can_use, const uint8_t* is_pos, const float* bbreg,
+                     const float* cls_pred, const float* reg_pred, int n_per_image, int batch, float* loss,
+                     float* grad_cls, float* grad_reg) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, can_use && is_pos && bbreg && cls_pred && reg_pred && loss, "rpn_losses: null pointer");
+  FRCNN_REQUIRE(h, n_per_image > 0 && batch > 0, "rpn_losses: non-positive size");
+  FRCNN_REQUIRE(h, ((reinterpret_cast<uintptr_t>(bbreg) | reinterpret_cast<uintptr_t>(reg_pred) |
+                     reinterpret_cast<uintptr_t>(grad_reg)) & 15) == 0, "rpn_losses: box arrays must be 16-byte aligned");
+  return launch_rpn_losses(h, st, can_use, is_pos, bbreg, cls_pred, reg_pred, n_per_image, batch, loss, grad_cls, grad_reg);
+}
+
+int frcnn_det_losses(frcnn_handle* h, void* stream, const int32_t* y_class, const float* y_transform,
+                     const float* cls_pred, const float* reg_pred, int m_rows, int n_classes, int batch, float* loss,
+                     float* grad_cls, float* grad_reg) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, y_class && y_transform && cls_pred && reg_pred && loss, "det_losses: null pointer");
+  FRCNN_REQUIRE(h, m_rows > 0 && n_classes >= 2 && batch > 0, "det_losses: bad size");
+  return launch_det_losses(h, st, y_class, y_transform, cls_pred, reg_pred, m_rows, n_classes, batch, loss, grad_cls,
+                           grad_reg);
 }
 
 }  // extern "C"

@@ -290,3 +290,38 @@ def pad_rois(rois, count, group=64, out=None):
         out, rows = ctx.empty((b, m, 4), torch.int16), ctx.empty((b,), torch.int32)
     ctx.call("frcnn_pad_rois", ptr(rois), ptr(count), n_max, int(group), m, b, ptr(out), ptr(rows))
     return out, rows
+
+
+def rpn_losses(can_use, is_pos, bbreg, cls_pred, reg_pred, want_grad=False):
+    """loss_functions.py:15-48 fused with the unpacked RPN labels.  can_use/is_pos (B,N) u8, bbreg (B,N,4) f32,
+    cls_pred (B,N) f32, reg_pred (B,N,4) f32 -> loss (B,2) f32 = (class, box) [, grad_cls (B,N), grad_reg (B,N,4)]."""
+    can_use, is_pos = _chk(can_use, torch.uint8, "can_use", 2), _chk(is_pos, torch.uint8, "is_pos", 2)
+    bbreg, reg_pred = _chk(bbreg, torch.float32, "bbreg", 3), _chk(reg_pred, torch.float32, "reg_pred", 3)
+    cls_pred = _chk(cls_pred, torch.float32, "cls_pred", 2)
+    ctx = get_context(can_use.device)
+    b, n = can_use.shape
+    if cls_pred.shape != (b, n) or bbreg.shape != (b, n, 4) or reg_pred.shape != (b, n, 4):
+        raise ValueError("rpn_losses: shapes must be (B,N), (B,N), (B,N,4), (B,N), (B,N,4)")
+    loss = ctx.empty((b, 2), torch.float32)
+    g_cls = ctx.empty((b, n), torch.float32) if want_grad else None
+    g_reg = ctx.empty((b, n, 4), torch.float32) if want_grad else None
+    ctx.call("frcnn_rpn_losses", ptr(can_use), ptr(is_pos), ptr(bbreg), ptr(cls_pred), ptr(reg_pred), n, b, ptr(loss),
+             ptr(g_cls), ptr(g_reg))
+    return (loss, g_cls, g_reg) if want_grad else loss
+
+
+def det_losses(y_class, y_transform, cls_pred, reg_pred, want_grad=False):
+    """loss_functions.py:51-76 on label_rois' targets.  y_class (B,M,K) i32, y_transform (B,M,8(K-1)) f32,
+    cls_pred (B,M,K) f32, reg_pred (B,M,4(K-1)) f32 -> loss (B,2) f32 = (class, box) [, grad_cls, grad_reg]."""
+    y_class, y_transform = _chk(y_class, torch.int32, "y_class", 3), _chk(y_transform, torch.float32, "y_transform", 3)
+    cls_pred, reg_pred = _chk(cls_pred, torch.float32, "cls_pred", 3), _chk(reg_pred, torch.float32, "reg_pred", 3)
+    ctx = get_context(y_class.device)
+    b, m, k = y_class.shape
+    if y_transform.shape != (b, m, 8 * (k - 1)) or cls_pred.shape != (b, m, k) or reg_pred.shape != (b, m, 4 * (k - 1)):
+        raise ValueError("det_losses: shapes must be (B,M,K), (B,M,8(K-1)), (B,M,K), (B,M,4(K-1))")
+    loss = ctx.empty((b, 2), torch.float32)
+    g_cls = ctx.empty((b, m, k), torch.float32) if want_grad else None
+    g_reg = ctx.empty((b, m, 4 * (k - 1)), torch.float32) if want_grad else None
+    ctx.call("frcnn_det_losses", ptr(y_class), ptr(y_transform), ptr(cls_pred), ptr(reg_pred), m, k, b, ptr(loss),
+             ptr(g_cls), ptr(g_reg))
+    return (loss, g_cls, g_reg) if want_grad else loss

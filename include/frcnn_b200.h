@@ -229,6 +229,26 @@ FRCNN_API int frcnn_valid_boxes(frcnn_handle* h, void* stream, const float* boxe
 FRCNN_API int frcnn_pad_rois(frcnn_handle* h, void* stream, const int16_t* rois, const int32_t* count,
                              int n_max, int group, int m_out, int batch, int16_t* out, int32_t* out_rows);
 
+/* ---- masked losses fused with the path's own targets (widening row)
+ * Replaces loss_functions.py:15-48 (cls_loss_rpn, bbreg_loss_rpn) and :51-76 (bbreg_loss_det,
+ * cls_loss_det), i.e. the Keras-backend expressions with binary_crossentropy / categorical_crossentropy
+ * of Keras 2.0.8 on TF 1.3.  loss [batch,2] receives the scalar Keras reports per output
+ * (RPN: class, box; detector: class, box); grad_* (optional, may be NULL) receive its gradient
+ * with respect to the predictions.
+ *   RPN: can_use / is_pos [batch,N] u8 and bbreg [batch,N,4] f32 are the UNPACKED labels
+ *   (frcnn_label_anchors + sampling), cls_pred [batch,N] f32 (sigmoid outputs, (R,C,A) order),
+ *   reg_pred [batch,N,4] f32.  The mask of the RPN box loss multiplies the summed smooth-L1
+ *   like the reference does (loss_functions.py:40-46).
+ *   Detector: y_class [batch,M,K] i32 one-hot, y_transform [batch,M,8(K-1)] f32 = [labels|targets]
+ *   (frcnn_label_rois), cls_pred [batch,M,K] f32, reg_pred [batch,M,4(K-1)] f32. */
+FRCNN_API int frcnn_rpn_losses(frcnn_handle* h, void* stream, const uint8_t* can_use, const uint8_t* is_pos,
+                               const float* bbreg, const float* cls_pred, const float* reg_pred,
+                               int n_per_image, int batch, float* loss, float* grad_cls, float* grad_reg);
+FRCNN_API int frcnn_det_losses(frcnn_handle* h, void* stream, const int32_t* y_class,
+                               const float* y_transform, const float* cls_pred, const float* reg_pred,
+                               int m_rows, int n_classes, int batch, float* loss, float* grad_cls,
+                               float* grad_reg);
+
 #ifdef __cplusplus
 }
 #endif
