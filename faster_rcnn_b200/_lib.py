@@ -43,6 +43,8 @@ SIGNATURES = {
     "frcnn_pad_rois": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "frcnn_rpn_losses": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "frcnn_det_losses": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "frcnn_voc_match": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _d, _p, _p]),
+    "frcnn_voc_pr_ap": (_i, [_p, _p, _p, _p, _i, _d, _p, _i, _p, _p, _p]),
 }
 
 _lib = None

@@ -38,6 +38,11 @@ int launch_rpn_losses(frcnn_handle*, cudaStream_t, const uint8_t*, const uint8_t
 int launch_det_losses(frcnn_handle*, cudaStream_t, const int32_t*, const float*, const float*, const float*, int, int,
                       int, float*, float*, float*);
 
+int launch_voc_match(frcnn_handle*, cudaStream_t, const double*, const int32_t*, const int32_t*, const double*,
+                     const uint8_t*, const int32_t*, int, double, uint8_t*, double*, double*);
+int launch_voc_pr_ap(frcnn_handle*, cudaStream_t, const double*, const double*, int, double, const double*, int, double*,
+                     double*, double*);
+
 // ---- scratch arena -------------------------------------------------------------------------
 // Bump allocator over one device block.  Every public entry point starts with arena_reset();
 // the launchers then carve their workspaces with arena_get().  When a call needs more than the
@@ -381,6 +386,31 @@ int frcnn_det_losses(frcnn_handle* h, void* stream, const int32_t* y_class, cons
   FRCNN_REQUIRE(h, m_rows > 0 && n_classes >= 2 && batch > 0, "det_losses: bad size");
   return launch_det_losses(h, st, y_class, y_transform, cls_pred, reg_pred, m_rows, n_classes, batch, loss, grad_cls,
                            grad_reg);
+}
+
+int frcnn_voc_match(frcnn_handle* h, void* stream, const double* det_boxes, const int32_t* img_det_offsets,
+                    const int32_t* img_det_rank, const double* gt_boxes, const uint8_t* gt_difficult,
+                    const int32_t* img_gt_offsets, int n_images, int n_dets, int n_gt, double ovthresh, double* tp,
+                    double* fp) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, img_det_offsets && img_gt_offsets && tp && fp, "voc_match: null pointer");
+  FRCNN_REQUIRE(h, n_images > 0 && n_dets >= 0 && n_gt >= 0, "voc_match: bad size");
+  FRCNN_REQUIRE(h, (n_dets == 0 || (det_boxes && img_det_rank)) && (n_gt == 0 || (gt_boxes && gt_difficult)),
+                "voc_match: null pointer");
+  if (n_dets == 0) return FRCNN_OK;
+  void* taken = nullptr;
+  int rc = arena_get(h, st, (size_t)(n_gt > 0 ? n_gt : 1), &taken);
+  if (rc) return rc;
+  return launch_voc_match(h, st, det_boxes, img_det_offsets, img_det_rank, gt_boxes, gt_difficult, img_gt_offsets,
+                          n_images, ovthresh, static_cast<uint8_t*>(taken), tp, fp);
+}
+
+int frcnn_voc_pr_ap(frcnn_handle* h, void* stream, const double* tp, const double* fp, int n_dets, double npos,
+                    const double* thresholds, int n_thresholds, double* rec, double* prec, double* ap) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, ap && thresholds && n_thresholds > 0, "voc_pr_ap: null pointer");
+  FRCNN_REQUIRE(h, n_dets >= 0 && (n_dets == 0 || (tp && fp && rec && prec)), "voc_pr_ap: null pointer");
+  return launch_voc_pr_ap(h, st, tp, fp, n_dets, npos, thresholds, n_thresholds, rec, prec, ap);
 }
 
 }  // extern "C"

@@ -325,3 +325,29 @@ def det_losses(y_class, y_transform, cls_pred, reg_pred, want_grad=False):
     ctx.call("frcnn_det_losses", ptr(y_class), ptr(y_transform), ptr(cls_pred), ptr(reg_pred), m, k, b, ptr(loss),
              ptr(g_cls), ptr(g_reg))
     return (loss, g_cls, g_reg) if want_grad else loss
+
+
+def voc_match(det_boxes, img_det_offsets, img_det_rank, gt_boxes, gt_difficult, img_gt_offsets, ovthresh=0.5):
+    """eval_dets.py:75-116 for one class.  det_boxes (nd,4) f64 sorted by descending confidence, CSR of detection
+    ranks per image, gt (ng,4) f64 + difficult (ng,) u8 grouped by image -> tp (nd,) f64, fp (nd,) f64."""
+    det_boxes, gt_boxes = _chk(det_boxes, torch.float64, "det_boxes", 2), _chk(gt_boxes, torch.float64, "gt_boxes", 2)
+    img_det_offsets, img_det_rank = _chk(img_det_offsets, torch.int32, "img_det_offsets", 1), _chk(img_det_rank, torch.int32, "img_det_rank", 1)
+    gt_difficult, img_gt_offsets = _chk(gt_difficult, torch.uint8, "gt_difficult", 1), _chk(img_gt_offsets, torch.int32, "img_gt_offsets", 1)
+    ctx = get_context(det_boxes.device)
+    nd, ng, n_img = det_boxes.shape[0], gt_boxes.shape[0], img_det_offsets.numel() - 1
+    tp, fp = ctx.empty((nd,), torch.float64), ctx.empty((nd,), torch.float64)
+    ctx.call("frcnn_voc_match", ptr(det_boxes), ptr(img_det_offsets), ptr(img_det_rank), ptr(gt_boxes), ptr(gt_difficult),
+             ptr(img_gt_offsets), n_img, nd, ng, float(ovthresh), ptr(tp), ptr(fp))
+    return tp, fp
+
+
+def voc_pr_ap(tp, fp, npos, thresholds):
+    """eval_dets.py:118-125 + the 11-point voc_ap (:8-19): -> rec (nd,), prec (nd,), ap (1,) all f64."""
+    tp, fp = _chk(tp, torch.float64, "tp", 1), _chk(fp, torch.float64, "fp", 1)
+    thresholds = _chk(thresholds, torch.float64, "thresholds", 1)
+    ctx = get_context(tp.device)
+    nd = tp.shape[0]
+    rec, prec, ap = ctx.empty((nd,), torch.float64), ctx.empty((nd,), torch.float64), ctx.empty((1,), torch.float64)
+    ctx.call("frcnn_voc_pr_ap", ptr(tp), ptr(fp), nd, float(npos), ptr(thresholds), thresholds.numel(), ptr(rec), ptr(prec),
+             ptr(ap))
+    return rec, prec, ap

@@ -249,6 +249,24 @@ FRCNN_API int frcnn_det_losses(frcnn_handle* h, void* stream, const int32_t* y_c
                                int m_rows, int n_classes, int batch, float* loss, float* grad_cls,
                                float* grad_reg);
 
+/* ---- VOC detection evaluation (widening row)
+ * Replaces the matching loop of eval_dets.voc_eval (eval_dets.py:75-116) and its precision /
+ * recall / 11-point AP arithmetic (eval_dets.py:118-125, voc_ap :8-19) for one class.
+ *   det_boxes [n_dets,4] f64 sorted by descending confidence; img_det_offsets [n_images+1] +
+ *   img_det_rank [n_dets]: CSR listing, per image, the ranks of its detections in ascending order;
+ *   gt_boxes [n_gt,4] f64 / gt_difficult [n_gt] u8 grouped by image with img_gt_offsets [n_images+1].
+ *   IoU uses the devkit's +1 convention in float64; tp / fp [n_dets] f64 are indexed by rank.
+ *   frcnn_voc_pr_ap: rec / prec [n_dets] f64 and ap [1] f64 = sum over thresholds [n_thresholds] f64
+ *   (device) of max(prec[rec >= t]) / n_thresholds (0 where no element qualifies). */
+FRCNN_API int frcnn_voc_match(frcnn_handle* h, void* stream, const double* det_boxes,
+                              const int32_t* img_det_offsets, const int32_t* img_det_rank,
+                              const double* gt_boxes, const uint8_t* gt_difficult,
+                              const int32_t* img_gt_offsets, int n_images, int n_dets, int n_gt,
+                              double ovthresh, double* tp, double* fp);
+FRCNN_API int frcnn_voc_pr_ap(frcnn_handle* h, void* stream, const double* tp, const double* fp, int n_dets,
+                              double npos, const double* thresholds, int n_thresholds, double* rec,
+                              double* prec, double* ap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,9 +91,56 @@ def voc_gt_case(ref, n_images=200):
          names=np.array(names), label_sha1=np.array(digests), n_pos=np.array(npos), n_use=np.array(nuse))
 
 
+def voc_eval_case(n_images=400):
+    """eval_dets.voc_eval (unmodified reference) on its own VOC_test annotations and synthetic detection files:
+    jittered copies of the ground truth (0-2 per object) plus random false positives, unique confidences."""
+    import contextlib
+    import io
+    import tempfile
+    sys.path.insert(0, ref_loader.REF_DIR)
+    import eval_dets as ref_eval
+    from data.voc_data_helpers import extract_img_data
+    root = '/root/reference/test_data/VOC_test'
+    names = [l.strip() for l in open(root + '/ImageSets/Main/trainval.txt')][:n_images]
+    rng = np.random.default_rng(7)
+    out = {'names': np.array(names)}
+    with tempfile.TemporaryDirectory() as tmp:
+        iset = os.path.join(tmp, 'set.txt')
+        open(iset, 'w').write('\n'.join(names) + '\n')
+        for cls in ('person', 'chair', 'car'):
+            lines, gt = [], {}
+            for nm in names:
+                objs = [b for b in extract_img_data(root, nm).gt_boxes if b.obj_cls == cls]
+                gt[nm] = (np.array([b.corners for b in objs]).reshape(-1, 4), np.array([b.difficult for b in objs], dtype=bool))
+                for b in objs:
+                    for _ in range(rng.integers(0, 3)):
+                        lines.append((nm, np.asarray(b.corners, float) + rng.normal(0, 6, 4)))
+                for _ in range(rng.integers(0, 3)):
+                    x1, y1 = rng.uniform(0, 300, 2)
+                    w, h = rng.uniform(10, 200, 2)
+                    lines.append((nm, np.array([x1, y1, x1 + w, y1 + h])))
+            conf = rng.permutation(len(lines)) / len(lines) + 1e-3
+            order = rng.permutation(len(lines))
+            det_file = os.path.join(tmp, 'comp3_det_test_%s.txt' % cls)
+            with open(det_file, 'w') as f:
+                for i in order:
+                    f.write("%s %r %r %r %r %r\n" % (lines[i][0], float(conf[i]), *[float(round(v, 1)) for v in lines[i][1]]))
+            with contextlib.redirect_stdout(io.StringIO()):
+                rec, prec, ap = ref_eval.voc_eval(root, det_file, iset, cls, ovthresh=0.5)
+            gnames = [n for n in names if len(gt[n][0])]
+            out.update({cls + '_ids': np.array([lines[i][0] for i in order]), cls + '_conf': np.array([conf[i] for i in order]),
+                        cls + '_boxes': np.array([np.round(lines[i][1], 1) for i in order]), cls + '_rec': rec,
+                        cls + '_prec': prec, cls + '_ap': ap, cls + '_gt_names': np.array(gnames),
+                        cls + '_gt_boxes': np.concatenate([gt[n][0] for n in gnames]).astype(np.float64),
+                        cls + '_gt_difficult': np.concatenate([gt[n][1] for n in gnames]),
+                        cls + '_gt_counts': np.array([len(gt[n][0]) for n in gnames])})
+    save("voc_eval", **out)
+
+
 def main():
     ref = ref_loader.load()
     voc_gt_case(ref)
+    voc_eval_case()
     # P1: anchor tables
     save("anchors", voc=ref.util.get_anchors([128, 256, 512]), default=ref.shared_constants.DEFAULT_ANCHORS,
          scales_voc=np.array([128, 256, 512]))

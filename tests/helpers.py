@@ -45,3 +45,17 @@ class FakeRpn:
 def flipped_rows(got, want):
     """rows where two integer-valued box arrays differ (decode flips caused by expf ulps)."""
     return np.where(np.any(got != want, axis=1))[0]
+
+
+def voc_eval_golden(cls):
+    """(image_ids, confidence, boxes, gt_by_image, imagenames, rec, prec, ap) of tests/golden/voc_eval.npz."""
+    g = golden("voc_eval")
+    gt, start = {}, 0
+    for name, cnt in zip(g[cls + "_gt_names"].tolist(), g[cls + "_gt_counts"].tolist()):
+        gt[name] = (g[cls + "_gt_boxes"][start:start + cnt], g[cls + "_gt_difficult"][start:start + cnt])
+        start += cnt
+    names = g["names"].tolist()
+    for name in names:
+        gt.setdefault(name, (np.zeros((0, 4)), np.zeros(0, bool)))
+    return (g[cls + "_ids"].tolist(), g[cls + "_conf"], g[cls + "_boxes"], gt, names, g[cls + "_rec"], g[cls + "_prec"],
+            float(g[cls + "_ap"]))
