@@ -143,6 +143,42 @@ def main():
         ms = timeit(lambda: ops.det_postprocess(rois, oc, orr, ratio, 20), args.iters)
         rec("det_postprocess", "C2 vgg16 320 rows 21 cls b64", ms, batch)
 
+    # ---- widening rows: masked losses (8f-2) and VOC evaluation (8f-3) ----------------------------------------------
+    if want("losses"):
+        batch, rows, cols = 128, 38, 63
+        n = rows * cols * 9
+        gts = np.stack([np.array([g[1:] for g in synth.gt_boxes(50, 1000, 600, 300 + i)], np.float32) for i in range(batch)])
+        cu, ip, bb, _ = ops.label_anchors(dev(gts), dev(np.full(batch, 50, np.int32)),
+                                          dev(np.tile(np.array([[1000, 600]], np.int32), (batch, 1))), rows, cols, voc, 16)
+        cp, rp = torch.rand((batch, n), device="cuda"), torch.randn((batch, n, 4), device="cuda")
+        ms = timeit(lambda: ops.rpn_losses(cu, ip, bb, cp, rp, want_grad=True), args.iters)
+        rec("rpn_losses+grad", "C4 voc b128", ms, batch, batch * n * (2 + 16 + 4 + 16 + 4 + 16))
+        yc = torch.zeros((batch, 64, 21), dtype=torch.int32, device="cuda")
+        yc[..., -1] = 1
+        yt = torch.zeros((batch, 64, 160), device="cuda")
+        pc, pr = torch.softmax(torch.randn((batch, 64, 21), device="cuda"), dim=2), torch.randn((batch, 64, 80), device="cuda")
+        ms = timeit(lambda: ops.det_losses(yc, yt, pc, pr, want_grad=True), args.iters)
+        rec("det_losses+grad", "64 rois 21 cls b128", ms, batch)
+    if want("voc_eval"):
+        rng = np.random.default_rng(0)
+        n_img, per_img_gt, per_img_det = 4952, 3, 12                      # VOC2007 test size, one class
+        g_xy = rng.uniform(0, 400, (n_img * per_img_gt, 2))
+        gt = np.concatenate([g_xy, g_xy + rng.uniform(20, 200, (n_img * per_img_gt, 2))], axis=1)
+        d_xy = rng.uniform(0, 400, (n_img * per_img_det, 2))
+        det = np.concatenate([d_xy, d_xy + rng.uniform(20, 200, (n_img * per_img_det, 2))], axis=1)
+        rank_img = rng.integers(0, n_img, n_img * per_img_det)
+        by_img = np.argsort(rank_img, kind='stable').astype(np.int32)
+        d_off = np.concatenate([[0], np.cumsum(np.bincount(rank_img, minlength=n_img))]).astype(np.int32)
+        g_off = (np.arange(n_img + 1) * per_img_gt).astype(np.int32)
+        a = [dev(det), dev(d_off), dev(by_img), dev(gt), dev(np.zeros(len(gt), np.uint8)), dev(g_off)]
+        thr = dev(np.arange(0., 1.1, 0.1))
+
+        def run():
+            tp, fp = ops.voc_match(*a, 0.5)
+            return ops.voc_pr_ap(tp, fp, float(len(gt)), thr)
+        ms = timeit(run, args.iters)
+        rec("voc_match+pr_ap", "4952 images x 12 dets x 3 gt, one class", ms, n_img)
+
     if args.json:
         os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
         json.dump(res, open(args.json, "w"), indent=1)

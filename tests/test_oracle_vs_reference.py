@@ -184,3 +184,34 @@ def test_known_answer_000005(ref):
     assert np.where(ip)[0].tolist() == [7454, 10586, 11036, 11486, 11963, 12413, 12863, 13079, 13529, 13680, 13979]
     assert int(cu.sum()) == 5287
     assert abs(float(np.abs(bb).sum()) - 33.408202) < 1e-4
+
+
+def test_voc_eval_live(ref, tmp_path):
+    """eval_dets.voc_eval (imports without Keras) run live on the reference's own annotations vs the eval oracle."""
+    import contextlib
+    import io
+    import sys
+    from oracle import eval_oracle as E
+    sys.path.insert(0, ref_loader.REF_DIR)
+    import eval_dets as ref_eval
+    root = '/root/reference/test_data/VOC_test'
+    names = [l.strip() for l in open(root + '/ImageSets/Main/trainval.txt')][400:520]
+    rng = np.random.default_rng(11)
+    iset = tmp_path / 'set.txt'
+    iset.write_text('\n'.join(names) + '\n')
+    lines, gt = [], {}
+    for nm in names:
+        objs = [b for b in ref.voc.extract_img_data(root, nm).gt_boxes if b.obj_cls == 'person']
+        gt[nm] = (np.array([b.corners for b in objs]).reshape(-1, 4), np.array([b.difficult for b in objs], dtype=bool))
+        for b in objs:
+            for _ in range(rng.integers(0, 3)):
+                lines.append((nm, np.round(np.asarray(b.corners, float) + rng.normal(0, 8, 4), 1)))
+        lines.append((nm, np.array([5., 5., 60., 80.])))
+    conf = rng.permutation(len(lines)) / len(lines)
+    det_file = tmp_path / 'comp3_det_test_person.txt'
+    det_file.write_text(''.join("%s %r %r %r %r %r\n" % (n, float(c), *[float(v) for v in b]) for (n, b), c in zip(lines, conf)))
+    with contextlib.redirect_stdout(io.StringIO()):
+        rec, prec, ap = ref_eval.voc_eval(root, str(det_file), str(iset), 'person', ovthresh=0.5)
+    r, p, a = E.voc_match([l[0] for l in lines], conf, np.array([l[1] for l in lines]), gt)
+    assert np.array_equal(r, rec) and np.array_equal(p, prec) and a == ap and ap > 0.05
+    assert E.voc_ap(rec, prec, False) == ref_eval.voc_ap(rec, prec, False)
