@@ -1,7 +1,8 @@
 // K-d: RoI layer (custom_layers.py:35-56) forward and backward, channels-last.
 //
-// A tiny pre-kernel turns the RoIs of a launch into tap tables (all int<->float conversions and
-// divisions of the layer, once per (RoI, output index)); the streaming kernels only index them.
+// All int<->float conversions and divisions of the layer (they run on the 16-lane XU pipe) happen once per
+// (RoI, output index) as "tap records": the forward CTA builds its RoI's records in shared memory in its
+// prologue, the backward launches a tiny pre-kernel that writes them for all RoIs (every cell needs them).
 //
 // Forward (both modes): one CTA per (RoI, 1024-channel block, image); a thread owns four
 // consecutive channels (128-bit loads/stores), walks the PxP outputs and streams them out with
@@ -66,6 +67,20 @@ __device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4
 //   taps[roi*P + p] = resize: (ylo | yhi << 16, bits(ylerp), xlo | xhi << 16, bits(xlerp))
 //                     max:    (ya  | yb  << 16, 0,           xa  | xb  << 16, 0)   [a, b) bounds
 // ---------------------------------------------------------------------------------------
+// one tap record of RoI crop `k` for output index p (see the table layout above)
+template <int MODE>
+__device__ __forceinline__ int4 make_tap(const Crop& k, int p, int P) {
+  if (k.w <= 0 || k.h <= 0) return make_int4(0, 0, 0, 0);
+  if (MODE == FRCNN_ROI_RESIZE) {
+    const Tap ty = axis_tap(p, (float)k.h / (float)P, k.h), tx = axis_tap(p, (float)k.w / (float)P, k.w);
+    return make_int4((k.y1 + ty.lo) | ((k.y1 + ty.hi) << 16), __float_as_int(ty.lerp),
+                     (k.x1 + tx.lo) | ((k.x1 + tx.hi) << 16), __float_as_int(tx.lerp));
+  }
+  const int ya = k.y1 + (p * k.h) / P, yb = k.y1 + ((p + 1) * k.h + P - 1) / P;
+  const int xa = k.x1 + (p * k.w) / P, xb = k.x1 + ((p + 1) * k.w + P - 1) / P;
+  return make_int4(ya | (yb << 16), 0, xa | (xb << 16), 0);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 roi_table_kernel(const void* __restrict__ rois, int dtype, int n_total, int W, int H, int P,
@@ -78,19 +93,7 @@ roi_table_kernel(const void* __restrict__ rois, int dtype, int n_total, int W, i
     crops[roi] = make_int4(k.x1, k.y1, k.w, k.h);
     return;
   }
-  int4 rec = make_int4(0, 0, 0, 0);
-  if (k.w > 0 && k.h > 0) {
-    if (MODE == FRCNN_ROI_RESIZE) {
-      const Tap ty = axis_tap(p, (float)k.h / (float)P, k.h), tx = axis_tap(p, (float)k.w / (float)P, k.w);
-      rec = make_int4((k.y1 + ty.lo) | ((k.y1 + ty.hi) << 16), __float_as_int(ty.lerp),
-                      (k.x1 + tx.lo) | ((k.x1 + tx.hi) << 16), __float_as_int(tx.lerp));
-    } else {
-      const int ya = k.y1 + (p * k.h) / P, yb = k.y1 + ((p + 1) * k.h + P - 1) / P;
-      const int xa = k.x1 + (p * k.w) / P, xb = k.x1 + ((p + 1) * k.w + P - 1) / P;
-      rec = make_int4(ya | (yb << 16), 0, xa | (xb << 16), 0);
-    }
-  }
-  taps[(size_t)roi * P + p] = rec;
+  taps[(size_t)roi * P + p] = make_tap<MODE>(k, p, P);
 }
 
 constexpr int ROI_FWD_THREADS = 256;
@@ -99,14 +102,18 @@ constexpr int ROI_MAX_TABLE_P = 32;     // table-driven kernels support pool siz
 // Forward: one CTA per (RoI, 1024-channel block, image); a thread owns four consecutive channels.
 template <int MODE>
 __global__ void __launch_bounds__(ROI_FWD_THREADS)
-roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const int4* __restrict__ crops,
-               const int4* __restrict__ taps, int N, int P, float* __restrict__ out, int* __restrict__ argmax) {
+roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* __restrict__ rois, int dtype,
+               int N, int P, float* __restrict__ out, int* __restrict__ argmax) {
   __shared__ int4 s_tap[ROI_MAX_TABLE_P];
   __shared__ int4 s_crop;
   const int r = blockIdx.x, img = blockIdx.z;
   const size_t roi = (size_t)img * N + r;
-  if (threadIdx.x < P) s_tap[threadIdx.x] = taps[roi * P + threadIdx.x];
-  if (threadIdx.x == 32) s_crop = crops[roi];
+  // the CTA's own tap table: P threads do all int<->float conversions / divisions of this RoI once
+  if (threadIdx.x <= P && threadIdx.x <= ROI_MAX_TABLE_P) {
+    const Crop k = load_crop(rois, dtype, roi, W, H);
+    if (threadIdx.x < P) s_tap[threadIdx.x] = make_tap<MODE>(k, threadIdx.x, P);
+    else s_crop = make_int4(k.x1, k.y1, k.w, k.h);
+  }
   __syncthreads();
   const int c = (blockIdx.y * ROI_FWD_THREADS + threadIdx.x) * 4;
   if (c >= C) return;
@@ -502,14 +509,11 @@ int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
   if (C % 4 == 0 && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768 && (reinterpret_cast<uintptr_t>(feat) % 16 == 0) &&
       (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
       (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0)) {
-    int4 *crops = nullptr, *taps = nullptr;
-    int rc = build_tables(h, stream, mode, rois, dtype, batch * N, W, H, P, &crops, &taps);
-    if (rc) return rc;
     dim3 grid(N, (C / 4 + ROI_FWD_THREADS - 1) / ROI_FWD_THREADS, batch);
     if (mode == FRCNN_ROI_RESIZE)
-      roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, crops, taps, N, P, out, argmax);
+      roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, out, argmax);
     else
-      roi_fwd_kernel<FRCNN_ROI_MAX><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, crops, taps, N, P, out, argmax);
+      roi_fwd_kernel<FRCNN_ROI_MAX><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, out, argmax);
   } else {
     dim3 grid(N, (C + 127) / 128, batch);
     if (mode == FRCNN_ROI_RESIZE)
