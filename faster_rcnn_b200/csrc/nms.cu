@@ -109,6 +109,8 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
 
   if (tid == 0) { s_unsorted = 0; s_nkept = 0; s_stop = 0; }
   __syncthreads();
+  // distributed shared memory may only be touched once every CTA of the cluster is running
+  if (cl > 1) cluster.sync();
 
   // ---- 1. visit order --------------------------------------------------------------------
   int bad = 0;
