@@ -274,6 +274,8 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
 #pragma unroll
   for (int j = 0; j < CPB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // The kernel is occupancy-sensitive (80 registers at CPB = 8): prefetching the next chunk's crops and the next
+  // covering RoI's tap record one step ahead costs 32 registers and was slower (1.59 ms vs 1.25 ms, profiles/README.md).
   for (int w0 = 0; w0 < N; w0 += 32) {
     const int r = w0 + lane;
     bool inside = false;
