@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
     ap.add_argument("--json", default="")
+    ap.add_argument("--modes", default="resize,max", help="RoI layer modes to time")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     want = lambda name: not only or any(name.startswith(o) for o in only)   # noqa: E731
@@ -103,7 +104,7 @@ def main():
         rois = dev(np.stack([synth.random_rois(n_rois, h, w, 7 + i) for i in range(batch)]))
         out_b = 4 * batch * n_rois * p * p * c
         in_b = 4 * batch * h * w * c + 8 * batch * n_rois
-        for mode in ("resize", "max"):
+        for mode in args.modes.split(","):
             if want("roi_fwd"):
                 ms = timeit(lambda: ops.roi_forward(feat, rois, p, mode), args.iters)
                 rec("roi_fwd_" + mode, "%s b%d" % (tag, batch), ms, batch, in_b + out_b * (2 if mode == "max" else 1))

@@ -4,7 +4,7 @@
 // (RoI, output index) as "tap records": the forward CTA builds its RoI's records in shared memory in its
 // prologue, the backward launches a tiny pre-kernel that writes them for all RoIs (every cell needs them).
 //
-// Forward (both modes): one CTA per (RoI, 1024-channel block, image); a thread owns four
+// Forward (both modes): one CTA per (RoI, 256-channel block, image); a thread owns four
 // consecutive channels (128-bit loads/stores), walks the PxP outputs and streams them out with
 // evict-first stores.  The feature map (9.8 MB at 38x63x1024) stays L2-resident, the P*P*C
 // outputs (401 MB at N=2000) are the HBM stream.
@@ -96,10 +96,12 @@ roi_table_kernel(const void* __restrict__ rois, int dtype, int n_total, int W, i
   taps[(size_t)roi * P + p] = make_tap<MODE>(k, p, P);
 }
 
-constexpr int ROI_FWD_THREADS = 256;
+// 64-thread CTAs (256 channels): measured 1-7 % faster than 256-thread CTAs at every batch size (finer-grained CTAs,
+// 23 instead of 5 resident per SM at 44 registers -> 46 instead of 40 warps, shorter tail at 2000 RoIs x 1 image).
+constexpr int ROI_FWD_THREADS = 64;
 constexpr int ROI_MAX_TABLE_P = 32;     // table-driven kernels support pool sizes up to 32
 
-// Forward: one CTA per (RoI, 1024-channel block, image); a thread owns four consecutive channels.
+// Forward: one CTA per (RoI, 256-channel block, image); a thread owns four consecutive channels.
 template <int MODE>
 __global__ void __launch_bounds__(ROI_FWD_THREADS)
 roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* __restrict__ rois, int dtype,
