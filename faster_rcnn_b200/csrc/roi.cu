@@ -156,12 +156,17 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
       const int ya = s_tap[ph].x & 0xffff, yb = s_tap[ph].x >> 16;
       for (int pw = 0; pw < P; ++pw) {
         const int xa = s_tap[pw].z & 0xffff, xb = s_tap[pw].z >> 16;
-        float4 best = ldg_f4(f + ((size_t)ya * W + xa) * C);
-        int4 arg = make_int4(ya * W + xa, ya * W + xa, ya * W + xa, ya * W + xa);
-        for (int y = ya; y < yb; ++y) {
-          for (int x = xa; x < xb; ++x) {
-            const float4 v = ldg_f4(f + ((size_t)y * W + x) * C);
-            const int cell = y * W + x;
+        // running pointers instead of per-cell 64-bit index arithmetic (8 of the 22 SASS instructions per cell)
+        const float* rp = f + ((size_t)ya * W + xa) * C;
+        int cell_row = ya * W + xa;
+        float4 best = ldg_f4(rp);
+        int4 arg = make_int4(cell_row, cell_row, cell_row, cell_row);
+        for (int y = ya; y < yb; ++y, rp += row_stride, cell_row += W) {
+          const float* cp = rp;
+          int cell = cell_row;
+#pragma unroll 4
+          for (int x = xa; x < xb; ++x, cp += C, ++cell) {
+            const float4 v = ldg_f4(cp);
             if (v.x > best.x) { best.x = v.x; arg.x = cell; }
             if (v.y > best.y) { best.y = v.y; arg.y = cell; }
             if (v.z > best.z) { best.z = v.z; arg.z = cell; }
@@ -258,7 +263,11 @@ __device__ __forceinline__ void cell_accumulate(int yc, int xc, float wy1, float
 #undef FRCNN_CELL_ACCUM
 }
 
-template <int CPB>
+// FULL: the CTA's CPB*128 channels all exist (C % (CPB*128) == 0): no per-load channel guards.  The per-bin
+// bookkeeping matters: in the first version of this loop 85 of the ~130 SASS instructions per bin were guards,
+// register zeroing and 64-bit address arithmetic (ncu source page), so the row address is kept as a per-RoI
+// pointer plus a 32-bit (ph, pw) offset.
+template <int CPB, bool FULL, int G>
 __global__ void __launch_bounds__(CW_WARPS * 32)
 roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restrict__ crops,
                            const int4* __restrict__ taps, int H, int W, int C, int N, int P,
@@ -269,9 +278,11 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
   const int img = blockIdx.z;
   const int y = cell / W, x = cell - y * W;
   const int cbase = blockIdx.y * (CPB * 128) + 4 * lane;
-  const float* g_img = gout + (size_t)img * N * P * P * C;
+  const float* g_lane = gout + (size_t)img * N * P * P * C + cbase;
   const int4* crop_img = crops + (size_t)img * N;
   const int4* tap_img = taps + (size_t)img * N * P;
+  const int row_floats = P * C;
+  const int sub = lane / G, p = lane % G;
   float4 acc[CPB];
 #pragma unroll
   for (int j = 0; j < CPB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -287,39 +298,57 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
     }
     unsigned m = __ballot_sync(0xffffffffu, inside);
     while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      // lane p looks at tap p of both axes; code bit0 = "lo tap is this cell", bit1 = "hi tap is this cell"
+      // Up to 32/G covering RoIs per pass: lane = G*sub + p looks at tap p (both axes) of the sub-th covering RoI;
+      // code bit0 = "lo tap is this cell", bit1 = "hi tap is this cell".  One table load and two ballots serve
+      // four RoIs when P <= 8 (the per-RoI scan was 40 % of this kernel's instructions).
+      int b = -1;
+      {
+        unsigned mm = m;
+#pragma unroll
+        for (int i = 0; i < 32 / G; ++i) {
+          const int bi = mm ? __ffs(mm) - 1 : -1;
+          if (sub == i) b = bi;
+          mm &= mm - 1;
+        }
+        m = mm;
+      }
       int ycode = 0, xcode = 0;
       int lyb = 0, lxb = 0;
-      if (lane < P) {
-        const int4 t = __ldg(tap_img + (size_t)(w0 + b) * P + lane);
+      if (b >= 0 && p < P) {
+        const int4 t = __ldg(tap_img + (w0 + b) * P + p);
         ycode = ((t.x & 0xffff) == y ? 1 : 0) | ((t.x >> 16) == y ? 2 : 0);
         xcode = ((t.z & 0xffff) == x ? 1 : 0) | ((t.z >> 16) == x ? 2 : 0);
         lyb = t.y;
         lxb = t.w;
       }
-      unsigned my = __ballot_sync(0xffffffffu, ycode != 0);
-      const unsigned mx = __ballot_sync(0xffffffffu, xcode != 0);
-      if (mx == 0u) continue;
-      const int roi_row = (w0 + b) * P;
-      while (my) {
-        const int ph = __ffs(my) - 1;
-        my &= my - 1;
-        const int yc = __shfl_sync(0xffffffffu, ycode, ph);
-        const int wyb = __shfl_sync(0xffffffffu, lyb, ph);
-        unsigned mxx = mx;
-        while (mxx) {
-          const int pw = __ffs(mxx) - 1;
-          mxx &= mxx - 1;
-          const int xc = __shfl_sync(0xffffffffu, xcode, pw);
-          const int wxb = __shfl_sync(0xffffffffu, lxb, pw);
-          const float* row = g_img + (size_t)((roi_row + ph) * P + pw) * C + cbase;
-          float4 g[CPB];
+      const unsigned by = __ballot_sync(0xffffffffu, ycode != 0);
+      const unsigned bx = __ballot_sync(0xffffffffu, xcode != 0);
 #pragma unroll
-          for (int j = 0; j < CPB; ++j)
-            g[j] = (cbase + j * 128 < C) ? ldg_f4(row + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-          cell_accumulate<CPB>(yc, xc, __int_as_float(wyb), __int_as_float(wxb), g, acc);
+      for (int i = 0; i < 32 / G; ++i) {
+        unsigned my = G == 32 ? by : (by >> (G * i % 32)) & ((1u << (G % 32)) - 1u);
+        const unsigned mx = G == 32 ? bx : (bx >> (G * i % 32)) & ((1u << (G % 32)) - 1u);
+        if (my == 0u || mx == 0u) continue;
+        const int bb = __shfl_sync(0xffffffffu, b, G * i % 32);
+        const float* g_roi = g_lane + (size_t)(w0 + bb) * P * row_floats;
+        while (my) {
+          const int ph = __ffs(my) - 1;
+          my &= my - 1;
+          const int yc = __shfl_sync(0xffffffffu, ycode, G * i % 32 + ph);
+          const int wyb = __shfl_sync(0xffffffffu, lyb, G * i % 32 + ph);
+          const int ph_off = ph * row_floats;
+          unsigned mxx = mx;
+          while (mxx) {
+            const int pw = __ffs(mxx) - 1;
+            mxx &= mxx - 1;
+            const int xc = __shfl_sync(0xffffffffu, xcode, G * i % 32 + pw);
+            const int wxb = __shfl_sync(0xffffffffu, lxb, G * i % 32 + pw);
+            const float* row = g_roi + (ph_off + pw * C);
+            float4 g[CPB];
+#pragma unroll
+            for (int j = 0; j < CPB; ++j)
+              g[j] = (FULL || cbase + j * 128 < C) ? ldg_f4(row + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cell_accumulate<CPB>(yc, xc, __int_as_float(wyb), __int_as_float(wxb), g, acc);
+          }
         }
       }
     }
@@ -340,7 +369,7 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
 // (A shared-memory tile-ownership kernel with per-tile work lists was the first version: 11.9 ms at
 // C1 x 64 images against 2.x ms for this one -- serial LDS/FADD/STS chains and 8 warps per SM.)
 // ---------------------------------------------------------------------------------------
-template <int CPB>
+template <int CPB, bool FULL, int G>
 __global__ void __launch_bounds__(CW_WARPS * 32)
 roi_bwd_max_cell_kernel(const float* __restrict__ gout, const int* __restrict__ argmax,
                         const int4* __restrict__ crops, const int4* __restrict__ taps, int H, int W, int C, int N,
@@ -351,11 +380,13 @@ roi_bwd_max_cell_kernel(const float* __restrict__ gout, const int* __restrict__ 
   const int img = blockIdx.z;
   const int y = cell / W, x = cell - y * W;
   const int cbase = blockIdx.y * (CPB * 128) + 4 * lane;
-  const size_t img_off = (size_t)img * N * P * P * C;
-  const float* g_img = gout + img_off;
-  const int* a_img = argmax + img_off;
+  const size_t img_off = (size_t)img * N * P * P * C + cbase;
+  const float* g_lane = gout + img_off;
+  const int* a_lane = argmax + img_off;
   const int4* crop_img = crops + (size_t)img * N;
   const int4* tap_img = taps + (size_t)img * N * P;
+  const int row_floats = P * C;
+  const int sub = lane / G, p = lane % G;
 
   float4 acc[CPB];
 #pragma unroll
@@ -370,41 +401,61 @@ roi_bwd_max_cell_kernel(const float* __restrict__ gout, const int* __restrict__ 
     }
     unsigned m = __ballot_sync(0xffffffffu, inside);
     while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
+      // 32/G covering RoIs per pass, lane = G*sub + p (see the resize kernel)
+      int b = -1;
+      {
+        unsigned mm = m;
+#pragma unroll
+        for (int i = 0; i < 32 / G; ++i) {
+          const int bi = mm ? __ffs(mm) - 1 : -1;
+          if (sub == i) b = bi;
+          mm &= mm - 1;
+        }
+        m = mm;
+      }
       bool hy = false, hx = false;
-      if (lane < P) {
-        const int4 t = __ldg(tap_img + (size_t)(w0 + b) * P + lane);
+      if (b >= 0 && p < P) {
+        const int4 t = __ldg(tap_img + (w0 + b) * P + p);
         hy = y >= (t.x & 0xffff) && y < (t.x >> 16);
         hx = x >= (t.z & 0xffff) && x < (t.z >> 16);
       }
-      unsigned my = __ballot_sync(0xffffffffu, hy);
-      const unsigned mx = __ballot_sync(0xffffffffu, hx);
-      const int roi_row = (w0 + b) * P;
-      while (my) {
-        const int ph = __ffs(my) - 1;
-        my &= my - 1;
-        unsigned mxx = mx;
-        while (mxx) {
-          const int pw = __ffs(mxx) - 1;
-          mxx &= mxx - 1;
-          const size_t o = (size_t)((roi_row + ph) * P + pw) * C + cbase;
-          // arg-max and dY rows are requested together (no dependent second round trip); a lane whose
-          // channels did not select this cell simply drops its dY values
-          int4 a[CPB];
-          float4 g[CPB];
+      const unsigned by = __ballot_sync(0xffffffffu, hy);
+      const unsigned bx = __ballot_sync(0xffffffffu, hx);
 #pragma unroll
-          for (int j = 0; j < CPB; ++j) {
-            const bool live = cbase + j * 128 < C;
-            a[j] = live ? __ldg(reinterpret_cast<const int4*>(a_img + o + j * 128)) : make_int4(-1, -1, -1, -1);
-            g[j] = live ? ldg_f4(g_img + o + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      for (int i = 0; i < 32 / G; ++i) {
+        unsigned my = G == 32 ? by : (by >> (G * i % 32)) & ((1u << (G % 32)) - 1u);
+        const unsigned mx = G == 32 ? bx : (bx >> (G * i % 32)) & ((1u << (G % 32)) - 1u);
+        if (my == 0u || mx == 0u) continue;
+        const int bb = __shfl_sync(0xffffffffu, b, G * i % 32);
+        const size_t roi_off = (size_t)(w0 + bb) * P * row_floats;
+        const float* g_roi = g_lane + roi_off;
+        const int* a_roi = a_lane + roi_off;
+        while (my) {
+          const int ph = __ffs(my) - 1;
+          my &= my - 1;
+          const int ph_off = ph * row_floats;
+          unsigned mxx = mx;
+          while (mxx) {
+            const int pw = __ffs(mxx) - 1;
+            mxx &= mxx - 1;
+            const int o = ph_off + pw * C;
+            // arg-max and dY rows are requested together (no dependent second round trip); a lane whose
+            // channels did not select this cell simply drops its dY values
+            int4 a[CPB];
+            float4 g[CPB];
 #pragma unroll
-          for (int j = 0; j < CPB; ++j) {
-            if (a[j].x == cell) acc[j].x += g[j].x;
-            if (a[j].y == cell) acc[j].y += g[j].y;
-            if (a[j].z == cell) acc[j].z += g[j].z;
-            if (a[j].w == cell) acc[j].w += g[j].w;
+            for (int j = 0; j < CPB; ++j) {
+              const bool live = FULL || cbase + j * 128 < C;
+              a[j] = live ? __ldg(reinterpret_cast<const int4*>(a_roi + o + j * 128)) : make_int4(-1, -1, -1, -1);
+              g[j] = live ? ldg_f4(g_roi + o + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < CPB; ++j) {
+              if (a[j].x == cell) acc[j].x += g[j].x;
+              if (a[j].y == cell) acc[j].y += g[j].y;
+              if (a[j].z == cell) acc[j].z += g[j].z;
+              if (a[j].w == cell) acc[j].w += g[j].w;
+            }
           }
         }
       }
@@ -544,10 +595,19 @@ int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
     if (cpb == 8 && (long long)H * W * batch < 2LL * h->sm_count * 32) cpb = 4;
     dim3 grid((H * W + CW_WARPS - 1) / CW_WARPS, (blocks128 + cpb - 1) / cpb, batch);
 #define FRCNN_LAUNCH_CELL(CPB)                                                                                      \
-  if (mode == FRCNN_ROI_RESIZE)                                                                                     \
-    roi_bwd_resize_cell_kernel<CPB><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);    \
+  if (mode == FRCNN_ROI_RESIZE) {                                                                                   \
+    if (C % (CPB * 128) == 0 && P <= 8)                                                                             \
+      roi_bwd_resize_cell_kernel<CPB, true, 8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);  \
+    else if (P <= 8)                                                                                                \
+      roi_bwd_resize_cell_kernel<CPB, false, 8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+    else                                                                                                            \
+      roi_bwd_resize_cell_kernel<CPB, false, 32><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+  } else if (C % (CPB * 128) == 0 && P <= 8)                                                                        \
+    roi_bwd_max_cell_kernel<CPB, true, 8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, argmax, crops, taps, H, W, C, N, P, gfeat); \
+  else if (P <= 8)                                                                                                  \
+    roi_bwd_max_cell_kernel<CPB, false, 8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, argmax, crops, taps, H, W, C, N, P, gfeat); \
   else                                                                                                              \
-    roi_bwd_max_cell_kernel<CPB><<<grid, CW_WARPS * 32, 0, stream>>>(gout, argmax, crops, taps, H, W, C, N, P, gfeat);
+    roi_bwd_max_cell_kernel<CPB, false, 32><<<grid, CW_WARPS * 32, 0, stream>>>(gout, argmax, crops, taps, H, W, C, N, P, gfeat);
     if (cpb == 8) { FRCNN_LAUNCH_CELL(8) } else if (cpb == 4) { FRCNN_LAUNCH_CELL(4) } else if (cpb == 2) { FRCNN_LAUNCH_CELL(2) } else { FRCNN_LAUNCH_CELL(1) }
 #undef FRCNN_LAUNCH_CELL
     FRCNN_LAUNCH_CHECK(h, "roi_bwd_cell_kernel");
