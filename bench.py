@@ -216,6 +216,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback. "
                          "Use --impl reference for the CPU arm.")
     torch.cuda.set_device(local_rank)
+    numa_cores = parallel.bind_to_gpu_numa(physical_gpu_index(local_rank)) if world > 1 else None
     parallel.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
     ctx = get_context(local_rank)
@@ -323,7 +324,8 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "image-sharded x%d, no hot-path collective, all-gather of final RoIs" % world,
                        "l2": "inputs larger than L2 (%.0f MB of features + %.0f MB of pooled output per step vs 126 MB L2)"
                              % (batch * ROWS * COLS * CHANNELS * 4 / 1e6, batch * PADDED * POOL * POOL * CHANNELS * 4 / 1e6),
-                       "rois_per_image": int(count0[0])},
+                       "rois_per_image": int(count0[0]),
+                       "host_affinity": ("rank 0 bound to %d GPU-local cores" % len(numa_cores)) if numa_cores else "unbound"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": pipe.h2d_bytes(cls_h, regr_h, feat_h), "d2h_bytes_per_step": pipe.d2h_bytes(batch),

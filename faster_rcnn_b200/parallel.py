@@ -27,6 +27,27 @@ def init_from_env(backend=None):
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pins this process to the CPU cores NVML reports as local to physical GPU `gpu_index`, BEFORE any pinned
+    staging buffer is allocated, so that first-touch places the buffers on the GPU's own NUMA node (with one
+    process per GPU, eight concurrent 655 MB uploads otherwise cross the socket interconnect).  Best effort:
+    returns the sorted core list it bound to, or None when NVML / the affinity call is unavailable or the
+    intersection with the allowed cores is empty (containers with a restricted cpuset)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cores = local & os.sched_getaffinity(0)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return sorted(cores)
+    except Exception:
+        return None
+
+
 def shard_range(n_items, rank, world):
     """Contiguous block [start, stop) of `n_items` owned by `rank`; blocks differ by at most one."""
     base, extra = divmod(n_items, world)
