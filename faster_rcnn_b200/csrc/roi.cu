@@ -105,24 +105,34 @@ constexpr int ROI_MAX_TABLE_P = 32;     // table-driven kernels support pool siz
 template <int MODE>
 __global__ void __launch_bounds__(ROI_FWD_THREADS)
 roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* __restrict__ rois, int dtype,
-               int N, int P, float* __restrict__ out, int* __restrict__ argmax) {
+               int N, int P, int ph_groups, float* __restrict__ out, int* __restrict__ argmax) {
   __shared__ int4 s_tap[ROI_MAX_TABLE_P];
+  __shared__ int4 s_xoff[ROI_MAX_TABLE_P];
   __shared__ int4 s_crop;
   const int r = blockIdx.x, img = blockIdx.z;
   const size_t roi = (size_t)img * N + r;
   // the CTA's own tap table: P threads do all int<->float conversions / divisions of this RoI once
   if (threadIdx.x <= P && threadIdx.x <= ROI_MAX_TABLE_P) {
     const Crop k = load_crop(rois, dtype, roi, W, H);
-    if (threadIdx.x < P) s_tap[threadIdx.x] = make_tap<MODE>(k, threadIdx.x, P);
-    else s_crop = make_int4(k.x1, k.y1, k.w, k.h);
+    if (threadIdx.x < P) {
+      const int4 t = make_tap<MODE>(k, threadIdx.x, P);
+      s_tap[threadIdx.x] = t;
+      s_xoff[threadIdx.x] = make_int4((t.z & 0xffff) * C * 4, (t.z >> 16) * C * 4, t.w, 0);
+    } else {
+      s_crop = make_int4(k.x1, k.y1, k.w, k.h);
+    }
   }
   __syncthreads();
-  const int c = (blockIdx.y * ROI_FWD_THREADS + threadIdx.x) * 4;
+  // blockIdx.y = channel block * ph_groups + group: small max-mode launches (2000 RoIs of ONE image are 2.7 waves of
+  // CTAs) are cut into P row groups per RoI so that the last wave is nearly full; everything else uses one group.
+  const int cblock = blockIdx.y / ph_groups, grp = blockIdx.y - cblock * ph_groups;
+  const int ph0 = grp * P / ph_groups, ph1 = (grp + 1) * P / ph_groups;
+  const int c = (cblock * ROI_FWD_THREADS + threadIdx.x) * 4;
   if (c >= C) return;
   const float* f = feat + (size_t)img * H * W * C + c;
   const size_t obase = (roi * P * P) * C + c;
   if (s_crop.z <= 0 || s_crop.w <= 0) {   // TF would raise on an empty crop; we emit zeros
-    for (int b = 0; b < P * P; ++b) {
+    for (int b = ph0 * P; b < ph1 * P; ++b) {
       st_cs_f4(out + obase + (size_t)b * C, make_float4(0.f, 0.f, 0.f, 0.f));
       if (MODE == FRCNN_ROI_MAX) st_cs_i4(argmax + obase + (size_t)b * C, make_int4(0, 0, 0, 0));
     }
@@ -130,10 +140,13 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
   }
   const size_t row_stride = (size_t)W * C;
   if (MODE == FRCNN_ROI_RESIZE) {
-    for (int ph = 0; ph < P; ++ph) {
+    // x taps as float offsets from the row pointer, once per thread: the per-output address arithmetic was 38 of the
+    // 80 SASS instructions of this loop (64-bit multiplies per tap), and this kernel runs into the 1000 W power cap
+    // in sustained operation (bench.py --steps 300: sw_power_cap, 0.96 -> 1.05 ms), so instructions are energy.
+    for (int ph = ph0; ph < ph1; ++ph) {
       const int4 ty = s_tap[ph];
-      const float* row_lo = f + (size_t)(ty.x & 0xffff) * row_stride;
-      const float* row_hi = f + (size_t)(ty.x >> 16) * row_stride;
+      const char* row_lo = reinterpret_cast<const char*>(f + (size_t)(ty.x & 0xffff) * row_stride);
+      const char* row_hi = reinterpret_cast<const char*>(f + (size_t)(ty.x >> 16) * row_stride);
       const float ly = __int_as_float(ty.y);
       float* o = out + obase + (size_t)ph * P * C;
       // Measured and rejected (profiles/README.md): L1-bypassing tap loads (ld.global.nc.L1::no_allocate and
@@ -141,18 +154,20 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
       // (no gain: the kernel is bound by L1/TEX + DRAM-write throughput, not load latency) and keeping
       // the last two source columns in registers (fewer loads, but the extra registers cost more
       // occupancy than the loads saved).
-      for (int pw = 0; pw < P; ++pw) {
-        const int4 tx = s_tap[pw];
-        const size_t xl = (size_t)(tx.z & 0xffff) * C, xh = (size_t)(tx.z >> 16) * C;
-        const float lx = __int_as_float(tx.w);
-        const float4 tl = ldg_f4(row_lo + xl), tr = ldg_f4(row_lo + xh);
-        const float4 bl = ldg_f4(row_hi + xl), br = ldg_f4(row_hi + xh);
+      for (int pw = 0; pw < P; ++pw, o += C) {
+        const int4 tx = s_xoff[pw];                 // (byte offset of xlo, of xhi, bits(lx), -), unsigned 32-bit
+        const float lx = __int_as_float(tx.z);
+        const unsigned bl_off = (unsigned)tx.x, bh_off = (unsigned)tx.y;
+        const float4 tl = ldg_f4(reinterpret_cast<const float*>(row_lo + bl_off));
+        const float4 tr = ldg_f4(reinterpret_cast<const float*>(row_lo + bh_off));
+        const float4 bl = ldg_f4(reinterpret_cast<const float*>(row_hi + bl_off));
+        const float4 br = ldg_f4(reinterpret_cast<const float*>(row_hi + bh_off));
         const float4 top = lerp4(tl, tr, lx), bot = lerp4(bl, br, lx);
-        st_cs_f4(o + (size_t)pw * C, lerp4(top, bot, ly));
+        st_cs_f4(o, lerp4(top, bot, ly));
       }
     }
   } else {
-    for (int ph = 0; ph < P; ++ph) {
+    for (int ph = ph0; ph < ph1; ++ph) {
       const int ya = s_tap[ph].x & 0xffff, yb = s_tap[ph].x >> 16;
       for (int pw = 0; pw < P; ++pw) {
         const int xa = s_tap[pw].z & 0xffff, xb = s_tap[pw].z >> 16;
@@ -561,14 +576,20 @@ static int build_tables(frcnn_handle* h, cudaStream_t stream, int mode, const vo
 
 int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* feat, int H, int W, int C,
                    const void* rois, int dtype, int N, int P, int batch, float* out, int32_t* argmax) {
-  if (C % 4 == 0 && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768 && (reinterpret_cast<uintptr_t>(feat) % 16 == 0) &&
+  if (C % 4 == 0 && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768 && (long long)W * C < (1LL << 29) &&
+      (reinterpret_cast<uintptr_t>(feat) % 16 == 0) &&
       (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
       (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0)) {
-    dim3 grid(N, (C / 4 + ROI_FWD_THREADS - 1) / ROI_FWD_THREADS, batch);
+    const int cblocks = (C / 4 + ROI_FWD_THREADS - 1) / ROI_FWD_THREADS;
+    // max mode, fewer than 8 waves of CTAs (20 resident per SM): split every RoI into P row groups (same-box A/B at
+    // 2000 RoIs x 1 image: 0.262 -> 0.232 ms; resize mode got slower with the split, 0.109 -> 0.117 ms, and keeps one)
+    const long long ctas = (long long)N * cblocks * batch;
+    const int ph_groups = (mode == FRCNN_ROI_MAX && ctas < 8LL * 20 * h->sm_count && (long long)cblocks * P <= 65535) ? P : 1;
+    dim3 grid(N, cblocks * ph_groups, batch);
     if (mode == FRCNN_ROI_RESIZE)
-      roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, out, argmax);
+      roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, ph_groups, out, argmax);
     else
-      roi_fwd_kernel<FRCNN_ROI_MAX><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, out, argmax);
+      roi_fwd_kernel<FRCNN_ROI_MAX><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, ph_groups, out, argmax);
   } else {
     dim3 grid(N, (C + 127) / 128, batch);
     if (mode == FRCNN_ROI_RESIZE)
