@@ -95,6 +95,30 @@ def test_roi_batch_and_pool_sizes(ops):
         assert np.abs(g[i] - want).max() <= 1e-5 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("b,h,w,c,n,pool", [
+    (4, 38, 63, 1024, 24, 7),     # >= 9472 cells: one warp per cell over all 1024 channels, no channel guards
+    (2, 14, 15, 384, 12, 7),      # 3 blocks of 128 channels: two channel chunks per cell, the second one partial
+    (2, 14, 15, 32, 9, 3),        # pool 3: four RoIs per scan pass with unused tap lanes
+    (2, 14, 15, 64, 9, 14),       # pool 14 > 8: one RoI per scan pass
+])
+def test_roi_backward_kernel_variants(ops, b, h, w, c, n, pool):
+    """Every template variant of the cell-stationary backward (channel span, guards, RoIs per scan pass), both modes."""
+    rng = np.random.default_rng(b * h + c + pool)
+    feat = rng.standard_normal((b, h, w, c), dtype=np.float32)
+    feat[:, ::3, ::2] = feat[0, 0, 0]                              # ties for the max mode
+    rois = np.stack([_rois(rng, n, h, w) for _ in range(b)])
+    gout = rng.standard_normal((b, n, pool, pool, c), dtype=np.float32)
+    g = host(ops.roi_backward(dev(gout), dev(rois), (b, h, w, c), "resize"))
+    out, arg = ops.roi_forward(dev(feat), dev(rois), pool, "max")
+    gm = host(ops.roi_backward(dev(gout), dev(rois), (b, h, w, c), "max", argmax=arg))
+    for i in range(b):
+        want = R.roi_resize_bwd(gout[i], rois[i], (h, w, c))
+        assert np.abs(g[i] - want).max() <= 1e-5 * np.abs(want).max()
+        wout, warg = R.roi_max_fwd(feat[i], rois[i], pool)
+        assert np.array_equal(host(out)[i], wout) and np.array_equal(host(arg)[i], warg)
+        assert np.array_equal(gm[i], R.roi_max_bwd(gout[i], warg, (h, w, c)))
+
+
 def test_roi_full_size_properties(ops):
     """C5 shape (38x63x1024, 2000 RoIs): <dY, fwd(X)> == <bwd(dY), X> (the backward is the exact adjoint of
     the forward), linearity of the forward, and a spot check of 16 RoIs against the oracle."""
