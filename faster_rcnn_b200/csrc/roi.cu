@@ -282,14 +282,24 @@ __device__ __forceinline__ void cell_accumulate(int yc, int xc, float wy1, float
 // bookkeeping matters: in the first version of this loop 85 of the ~130 SASS instructions per bin were guards,
 // register zeroing and 64-bit address arithmetic (ncu source page), so the row address is kept as a per-RoI
 // pointer plus a 32-bit (ph, pw) offset.
-template <int CPB, bool FULL, int G>
+// RS > 1 (small launches, e.g. 2000 RoIs of ONE image): RS warps share a cell, each walks a contiguous 1/RS of the
+// RoI chunks, and the partial sums are added in part order through shared memory.  With one image the launch is a
+// single wave whose duration is the longest chain (the busiest cells see twice the average number of RoIs); the
+// split shortens that chain RS-fold (0.335 -> 0.246 ms at 2000 RoIs x 1 image; RS = 2 / 8 and 512-channel warps were
+// measured too: 0.31 / 0.24 ms -- beyond RS = 4 the launch is bound by resident warps x bytes in flight, not by the
+// longest chain).  The summation order is still fixed (deterministic), just not the RS = 1 order.
+template <int CPB, bool FULL, int G, int RS>
 __global__ void __launch_bounds__(CW_WARPS * 32)
 roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restrict__ crops,
                            const int4* __restrict__ taps, int H, int W, int C, int N, int P,
                            float* __restrict__ gfeat) {
+  __shared__ float4 s_part[RS > 1 ? CW_WARPS * CPB * 32 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cell = blockIdx.x * CW_WARPS + warp;
-  if (cell >= H * W) return;                        // warp-uniform; the kernel has no block-level barrier
+  const int part = warp % RS;
+  const int cell_raw = blockIdx.x * (CW_WARPS / RS) + warp / RS;
+  const bool live = cell_raw < H * W;
+  if (RS == 1 && !live) return;                     // warp-uniform; the RS = 1 kernel has no block-level barrier
+  const int cell = live ? cell_raw : 0;
   const int img = blockIdx.z;
   const int y = cell / W, x = cell - y * W;
   const int cbase = blockIdx.y * (CPB * 128) + 4 * lane;
@@ -304,10 +314,13 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
 
   // The kernel is occupancy-sensitive (80 registers at CPB = 8): prefetching the next chunk's crops and the next
   // covering RoI's tap record one step ahead costs 32 registers and was slower (1.59 ms vs 1.25 ms, profiles/README.md).
-  for (int w0 = 0; w0 < N; w0 += 32) {
+  const int chunks = (N + 31) / 32, per_part = (chunks + RS - 1) / RS;
+  const int w_begin = RS == 1 ? 0 : part * per_part * 32;
+  const int w_end = RS == 1 ? N : (live ? min(N, (part + 1) * per_part * 32) : 0);
+  for (int w0 = w_begin; w0 < w_end; w0 += 32) {
     const int r = w0 + lane;
     bool inside = false;
-    if (r < N) {
+    if (r < w_end) {
       const int4 k = __ldg(crop_img + r);
       inside = k.z > 0 && k.w > 0 && x >= k.x && x < k.x + k.z && y >= k.y && y < k.y + k.w;
     }
@@ -368,6 +381,19 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
       }
     }
   }
+  if (RS > 1) {
+#pragma unroll
+    for (int j = 0; j < CPB; ++j) s_part[(warp * CPB + j) * 32 + lane] = acc[j];
+    __syncthreads();
+    if (part != 0 || !live) return;
+#pragma unroll
+    for (int q = 1; q < RS; ++q)
+#pragma unroll
+      for (int j = 0; j < CPB; ++j) {
+        const float4 v = s_part[((warp + q) * CPB + j) * 32 + lane];
+        acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+      }
+  }
   float* dst = gfeat + ((size_t)img * H * W + cell) * C + cbase;
 #pragma unroll
   for (int j = 0; j < CPB; ++j)
@@ -384,8 +410,11 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
 // (A shared-memory tile-ownership kernel with per-tile work lists was the first version: 11.9 ms at
 // C1 x 64 images against 2.x ms for this one -- serial LDS/FADD/STS chains and 8 warps per SM.)
 // ---------------------------------------------------------------------------------------
+// The kernel waits on its arg-max / dY round trips (ncu: issue 26 %, long-scoreboard stalls 17 per issue), so resident
+// warps buy throughput: the 512-channel variant used for small launches is capped at 64 registers (4 CTAs per SM;
+// 2000 RoIs x 1 image: 0.54 -> 0.36 ms).  The same cap on the 1024-channel variant spills and was 5 % slower at 8 images.
 template <int CPB, bool FULL, int G>
-__global__ void __launch_bounds__(CW_WARPS * 32)
+__global__ void __launch_bounds__(CW_WARPS * 32, CPB == 8 ? 0 : 4)
 roi_bwd_max_cell_kernel(const float* __restrict__ gout, const int* __restrict__ argmax,
                         const int4* __restrict__ crops, const int4* __restrict__ taps, int H, int W, int C, int N,
                         int P, float* __restrict__ gfeat) {
@@ -613,16 +642,24 @@ int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
     // channel blocks per warp: 8 (one warp per cell at C = 1024) when the launch has enough cells to fill
     // the GPU, else 4 so that a single image still yields >= 32 warps per SM
     int cpb = blocks128 >= 8 ? 8 : (blocks128 >= 4 ? 4 : (blocks128 >= 2 ? 2 : 1));
-    if (cpb == 8 && (long long)H * W * batch < 2LL * h->sm_count * 32) cpb = 4;
-    dim3 grid((H * W + CW_WARPS - 1) / CW_WARPS, (blocks128 + cpb - 1) / cpb, batch);
+    // resize mode, fewer than ~4 waves of warps and enough RoI chunks to share: four warps per cell (RS = 4)
+    const long long cell_warps = (long long)H * W * batch * ((blocks128 + cpb - 1) / cpb);
+    const bool split = mode == FRCNN_ROI_RESIZE && P <= 8 && cell_warps < 4LL * h->sm_count * 24 && N >= 256;
+    if (!split && cpb == 8 && (long long)H * W * batch < 2LL * h->sm_count * 32) cpb = 4;
+    const int cells_per_cta = split ? CW_WARPS / 4 : CW_WARPS;
+    dim3 grid((H * W + cells_per_cta - 1) / cells_per_cta, (blocks128 + cpb - 1) / cpb, batch);
 #define FRCNN_LAUNCH_CELL(CPB)                                                                                      \
   if (mode == FRCNN_ROI_RESIZE) {                                                                                   \
-    if (C % (CPB * 128) == 0 && P <= 8)                                                                             \
-      roi_bwd_resize_cell_kernel<CPB, true, 8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);  \
+    if (split && C % (CPB * 128) == 0)                                                                              \
+      roi_bwd_resize_cell_kernel<CPB, true, 8, 4><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+    else if (split)                                                                                                 \
+      roi_bwd_resize_cell_kernel<CPB, false, 8, 4><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+    else if (C % (CPB * 128) == 0 && P <= 8)                                                                        \
+      roi_bwd_resize_cell_kernel<CPB, true, 8, 1><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);  \
     else if (P <= 8)                                                                                                \
-      roi_bwd_resize_cell_kernel<CPB, false, 8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+      roi_bwd_resize_cell_kernel<CPB, false, 8, 1><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
     else                                                                                                            \
-      roi_bwd_resize_cell_kernel<CPB, false, 32><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+      roi_bwd_resize_cell_kernel<CPB, false, 32, 1><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
   } else if (C % (CPB * 128) == 0 && P <= 8)                                                                        \
     roi_bwd_max_cell_kernel<CPB, true, 8><<<grid, CW_WARPS * 32, 0, stream>>>(gout, argmax, crops, taps, H, W, C, N, P, gfeat); \
   else if (P <= 8)                                                                                                  \

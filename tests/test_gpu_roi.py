@@ -100,6 +100,8 @@ def test_roi_batch_and_pool_sizes(ops):
     (2, 14, 15, 384, 12, 7),      # 3 blocks of 128 channels: two channel chunks per cell, the second one partial
     (2, 14, 15, 32, 9, 3),        # pool 3: four RoIs per scan pass with unused tap lanes
     (2, 14, 15, 64, 9, 14),       # pool 14 > 8: one RoI per scan pass
+    (1, 12, 17, 128, 300, 7),     # small launch with >= 256 RoIs: four warps share a cell, each a quarter of the RoIs
+    (1, 9, 11, 1024, 257, 7),     # same with 1024 channels per warp and a ragged last quarter
 ])
 def test_roi_backward_kernel_variants(ops, b, h, w, c, n, pool):
     """Every template variant of the cell-stationary backward (channel span, guards, RoIs per scan pass), both modes."""
