@@ -129,6 +129,20 @@ def main():
                 del gout, arg
         del feat
 
+    # ---- device-resident pipeline (decode -> top-k -> NMS -> pad -> RoI layer), eager launches vs one CUDA graph ------
+    if want("pipeline"):
+        from faster_rcnn_b200.pipeline import ProposalRoiPipeline
+        pipe = ProposalRoiPipeline(voc, 16, 8000, 0.7, 300, 64, 7, "resize")
+        for batch in (1, 8, 64):
+            cls, regr = rpn_batch(38, 63, voc, batch, 100, False)
+            feat = torch.randn((batch, 38, 63, 1024), device="cuda")
+            ms = timeit(lambda: pipe.run_device(cls, regr, feat), args.iters)
+            rec("pipeline_eager", "C1 b%d" % batch, ms, batch)
+            run = pipe.capture(cls, regr, feat)
+            ms = timeit(lambda: run(), args.iters)
+            rec("pipeline_graph", "C1 b%d" % batch, ms, batch)
+            del run, feat
+
     # ---- C4 training targets: batch 128, 50 GT ---------------------------------------------------------------------
     if want("label"):
         batch, rows, cols = 128, 38, 63

@@ -52,6 +52,12 @@ class ProposalRoiPipeline:
         pooled = ops.roi_forward(feat, padded, self.pool_size, self.mode)
         return rois, scores, count, padded, pooled
 
+    def capture(self, cls, regr, feat):
+        """CUDA-graph capture of `run_device` for fixed shapes: returns a `GraphedRun` whose call copies
+        new inputs into the captured buffers and replays decode -> top-k -> NMS -> pad -> RoI layer as ONE graph
+        launch (5 kernels, no per-kernel Python/ctypes/launch overhead -- what matters at batch 1)."""
+        return GraphedRun(self, cls, regr, feat)
+
     def __call__(self, cls, regr, feat, on_device=None):
         """Host (or device) arrays in; returns (rois, scores, count) as numpy on the host -- what
         `get_det_inputs` hands back in the reference -- plus the pooled features as a CUDA tensor,
@@ -134,6 +140,36 @@ class ProposalRoiPipeline:
 
     def d2h_bytes(self, batch):
         return batch * (self.max_boxes * 8 + self.max_boxes * 4 + 4)
+
+
+class GraphedRun:
+    """One captured `ProposalRoiPipeline.run_device` call.  The graph runs on a private C-ABI handle: its scratch arena
+    is sized by two eager warm-up runs and can never be moved by other calls, so the device pointers baked into the
+    graph stay valid.  Outputs are the captured tensors (overwritten by every replay)."""
+
+    def __init__(self, pipe, cls, regr, feat):
+        from .runtime import Context, use_context
+        dev = pipe.ctx.device
+        self.inputs = tuple(torch.empty_like(t, device=dev).copy_(t) for t in (cls, regr, feat))
+        self._ctx = Context(dev.index)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with use_context(self._ctx), torch.cuda.stream(side):
+            for _ in range(2):                       # grows the private arena to its final size (merge on 2nd call)
+                pipe.run_device(*self.inputs)
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.outputs = pipe.run_device(*self.inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def __call__(self, cls=None, regr=None, feat=None):
+        """Replays the graph (after copying any given CUDA tensor into the captured input of the same shape)."""
+        for dst, src in zip(self.inputs, (cls, regr, feat)):
+            if src is not None and src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
 
 
 class DetectionPipeline(ProposalRoiPipeline):

@@ -107,6 +107,28 @@ def get_context(device=None):
         return ctx
 
 
+class use_context:
+    """`with use_context(ctx):` makes `get_context(ctx.device)` return `ctx` inside the block.  Used to run (and
+    capture) a sequence of ops on a PRIVATE handle whose scratch arena nobody else can grow or move afterwards."""
+
+    def __init__(self, ctx):
+        self.ctx, self.prev = ctx, None
+
+    def __enter__(self):
+        with _lock:
+            self.prev = _contexts.get(self.ctx.device.index)
+            _contexts[self.ctx.device.index] = self.ctx
+        return self.ctx
+
+    def __exit__(self, *exc):
+        with _lock:
+            if self.prev is None:
+                _contexts.pop(self.ctx.device.index, None)
+            else:
+                _contexts[self.ctx.device.index] = self.prev
+        return False
+
+
 def ptr(t):
     """Device pointer of a contiguous tensor (None -> NULL)."""
     if t is None:

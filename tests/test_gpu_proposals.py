@@ -312,3 +312,31 @@ def test_pipeline_host_staged_equals_device_path(ops):
     from oracle import roi_oracle as R
     n0 = int(count[0])
     assert np.array_equal(host(pooled)[0, :n0], R.roi_resize_fwd(feat[0], rois[0, :n0], 7))
+
+
+def test_pipeline_cuda_graph_replay_equals_eager(ops):
+    """ProposalRoiPipeline.capture: one graph launch per step, same rois / counts / pooled features as the eager path,
+    also after the inputs change and after other calls have used (and grown) the shared handle's arena."""
+    import torch
+    from faster_rcnn_b200 import synth
+    from faster_rcnn_b200.pipeline import ProposalRoiPipeline
+    from faster_rcnn_b200.util import get_anchors
+    dims = get_anchors([128, 256, 512])
+    rows, cols, ch, b = 19, 25, 64, 3
+    pipe = ProposalRoiPipeline(dims, 16, 2000, 0.7, 300, 64, 7, "resize")
+
+    def inputs(seed):
+        pairs = [synth.rpn_outputs(rows, cols, len(dims), seed + i, clustered=True) for i in range(b)]
+        return (dev(np.concatenate([p[0] for p in pairs])), dev(np.concatenate([p[1] for p in pairs])),
+                torch.randn((b, rows, cols, ch), device="cuda", generator=torch.Generator("cuda").manual_seed(seed)))
+
+    a = inputs(10)
+    run = pipe.capture(*a)
+    for seed in (10, 20):
+        x = inputs(seed)
+        want = [t.clone() for t in pipe.run_device(*x)]
+        ops.proposals(*inputs(99)[1::-1], dims, 16, 8000, 0.7, 300)          # unrelated call on the shared handle
+        got = run(*x)
+        torch.cuda.synchronize()
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)
