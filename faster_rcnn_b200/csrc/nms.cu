@@ -256,16 +256,31 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
       const unsigned long long rm_lo = row_mask[lane], rm_hi = row_mask[lane + 32];
       unsigned long long alive = ~supk;
       if (tile_n < 64) alive &= (1ull << tile_n) - 1ull;
-      unsigned long long keepbits = 0ull;
+      // Only candidates whose row mask hits a live candidate can change the outcome; visiting just those, in
+      // order, gives the greedy result (a row mask holds later candidates only).  With few overlaps inside a tile
+      // (the inference setting: 300 of the first ~330 candidates survive) this is a handful of steps instead of 64
+      // dependent ones -- the other 15 warps wait at the barrier below meanwhile (37 % of the kernel's stall samples).
       int room = max_boxes - nkept;
-      while (alive && room > 0) {
-        const int i = __ffsll((long long)alive) - 1;
+      const unsigned act_lo = __ballot_sync(0xffffffffu, ((alive >> lane) & 1ull) && (rm_lo & alive) != 0ull);
+      const unsigned act_hi = __ballot_sync(0xffffffffu, ((alive >> (lane + 32)) & 1ull) && (rm_hi & alive) != 0ull);
+      unsigned long long active = ((unsigned long long)act_hi << 32) | act_lo;
+      while (active) {
+        const int i = __ffsll((long long)active) - 1;
+        active &= active - 1ull;
         const unsigned long long rlo = __shfl_sync(0xffffffffu, rm_lo, i & 31), rhi = __shfl_sync(0xffffffffu, rm_hi, i & 31);
-        keepbits |= 1ull << i;
-        alive &= ~((i < 32) ? rlo : rhi);
-        alive &= ~(1ull << i);
-        --room;
+        if ((alive >> i) & 1ull) alive &= ~((i < 32) ? rlo : rhi);
       }
+      // survivors beyond the remaining room are not picked (the sweep stops there)
+      unsigned long long keepbits = room > 0 ? alive : 0ull;
+      if (room > 0 && __popcll(alive) > room) {
+        const unsigned lo = (unsigned)alive, hi = (unsigned)(alive >> 32);
+        const int nlo = __popc(lo);
+        int last;                                   // position of the room-th live bit (room >= 1 here)
+        if (room <= nlo) last = (int)__fns(lo, 0, room);
+        else last = 32 + (int)__fns(hi, 0, room - nlo);
+        keepbits = alive & ((last >= 63) ? ~0ull : ((1ull << (last + 1)) - 1ull));
+      }
+      room -= __popcll(keepbits);
       if (lane == 0) {
         s_keepbits = keepbits;
         s_nkept = nkept + __popcll(keepbits);
