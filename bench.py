@@ -241,6 +241,13 @@ def run_ours(args, rank, world, local_rank):
     def step(events=None):
         rois, scores, count = pipe_ops.proposals(regr, cls, dims, STRIDE, TOPK, NMS_THRESH, MAX_BOXES)
         padded, _ = pipe_ops.pad_rois(rois, count, NUM_ROIS)
+        pending = None
+        if world > 1:      # the path's only exchange: final RoIs + counts, one all-gather each per step, issued
+            #                before the RoI layer (which needs only the local RoIs) so that NCCL runs next to it
+            if "rois" not in gathered:
+                gathered["rois"] = torch.empty((world * batch, MAX_BOXES, 4), dtype=torch.int16, device=dev)
+                gathered["count"] = torch.empty((world * batch,), dtype=torch.int32, device=dev)
+            _, _, pending = parallel.all_gather_rois(rois, count, gathered["rois"], gathered["count"], async_op=True)
         if events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -248,11 +255,8 @@ def run_ours(args, rank, world, local_rank):
         if events is not None:
             e1.record()
             events.append((e0, e1))
-        if world > 1:      # the path's only exchange: final RoIs + counts, one all-gather each per step
-            if "rois" not in gathered:
-                gathered["rois"] = torch.empty((world * batch, MAX_BOXES, 4), dtype=torch.int16, device=dev)
-                gathered["count"] = torch.empty((world * batch,), dtype=torch.int32, device=dev)
-            parallel.all_gather_rois(rois, count, gathered["rois"], gathered["count"])
+        if pending is not None:
+            pending.wait()
         return rois, count, pooled
 
     from faster_rcnn_b200 import ops as pipe_ops

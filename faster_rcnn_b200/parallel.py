@@ -77,17 +77,32 @@ def all_gather_detections(dets, counts, group=None):
     return out_d, out_c
 
 
-def all_gather_rois(rois, count, out_rois=None, out_count=None, group=None):
+class _Pending:
+    """Handles of collectives issued with async_op=True; `wait()` makes the current stream wait for them."""
+
+    def __init__(self, works):
+        self.works = works
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+
+
+def all_gather_rois(rois, count, out_rois=None, out_count=None, group=None, async_op=False):
     """All-gather of the proposal stage's result: rois (b,max_boxes,4) int16 + count (b,) int32 ->
     (world*b, max_boxes, 4) int16, (world*b,) int32.  NCCL has no int16 type, so the RoI rows travel
-    as int32 pairs (a reinterpreting view, no copy).  `out_*` may be preallocated buffers."""
+    as int32 pairs (a reinterpreting view, no copy).  `out_*` may be preallocated buffers.
+    `async_op=True` returns (out_rois, out_count, pending): the exchange runs on NCCL's stream next to whatever
+    is enqueued afterwards (the RoI layer needs only the LOCAL RoIs); call `pending.wait()` before the gathered
+    buffers are read."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return rois, count
+        return (rois, count, _Pending([])) if async_op else (rois, count)
     world = dist.get_world_size(group)
     if out_rois is None:
         out_rois = torch.empty((world * rois.shape[0],) + tuple(rois.shape[1:]), dtype=rois.dtype, device=rois.device)
     if out_count is None:
         out_count = torch.empty((world * count.shape[0],), dtype=count.dtype, device=count.device)
-    dist.all_gather_into_tensor(out_rois.view(torch.int32), rois.contiguous().view(torch.int32), group=group)
-    dist.all_gather_into_tensor(out_count, count.contiguous(), group=group)
-    return out_rois, out_count
+    w1 = dist.all_gather_into_tensor(out_rois.view(torch.int32), rois.contiguous().view(torch.int32), group=group,
+                                     async_op=async_op)
+    w2 = dist.all_gather_into_tensor(out_count, count.contiguous(), group=group, async_op=async_op)
+    return (out_rois, out_count, _Pending([w1, w2])) if async_op else (out_rois, out_count)

@@ -49,6 +49,10 @@ def _worker(rank, world, port, n_images, out_dir):
     g_rois, g_cnt = parallel.all_gather_rois(rois, torch.full((stop - start,), rank, dtype=torch.int32))
     assert g_rois.dtype == torch.int16 and g_rois.shape == (n_images, 5, 4)
     assert torch.equal(g_rois[start:stop], rois) and g_cnt.tolist() == [0] * (n_images // 2) + [1] * (n_images // 2)
+    # asynchronous form (overlaps the RoI layer in bench.py): same buffers after pending.wait()
+    a_rois, a_cnt, pending = parallel.all_gather_rois(rois, torch.full((stop - start,), rank, dtype=torch.int32), async_op=True)
+    pending.wait()
+    assert torch.equal(a_rois, g_rois) and torch.equal(a_cnt, g_cnt)
     torch.save((all_d, all_c), os.path.join(out_dir, "rank%d.pt" % rank))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
