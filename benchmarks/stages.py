@@ -161,6 +161,25 @@ def main():
         ms = timeit(lambda: ops.label_rois(rois, gt64, gcls, n_gt, 21), args.iters)
         rec("label_rois", "C4 2000 rois 50gt b128", ms, batch, batch * 2000 * (8 + 8 + 84 + 640 + 4))
 
+    # ---- C4 detector-training inputs, batch 128: proposals 12000 -> 2000, RoI x GT labelling, host draw, gather, RoI layer
+    if want("det_training"):
+        from faster_rcnn_b200.pipeline import DetTrainingPipeline
+        batch, rows, cols = 128, 38, 63
+        cls, regr = rpn_batch(rows, cols, voc, batch, 700, True)
+        feat = torch.randn((batch, rows, cols, 1024), device="cuda")
+        gts = np.stack([np.array([g[1:] for g in synth.gt_boxes(50, 1000, 600, 300 + i)], np.float64) for i in range(batch)]) / 16
+        gt, n_gt = dev(gts), dev(np.full(batch, 50, np.int32))
+        gcls = dev(np.tile(np.arange(50, dtype=np.int32) % 20, (batch, 1)))
+        pipe = DetTrainingPipeline(synth.VOC_CLASS_MAPPING, voc)
+        np.random.seed(0)
+
+        def run():
+            r, yc, yt, _ = pipe.targets(cls, regr, gt, gcls, n_gt)
+            return ops.roi_forward(feat, r, 7, "resize")
+        ms = timeit(run, max(3, args.iters // 4), 2)
+        rec("det_training_inputs+roi_fwd", "C4 voc 12000->2000, 50 gt, 64 samples b128 (incl. host RNG draw)", ms, batch)
+        del feat
+
     # ---- C2 detector post-processing: 64 images x 320 rows x 21 classes ------------------------------------------------
     if want("postprocess"):
         batch = 64

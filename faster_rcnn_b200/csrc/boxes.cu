@@ -145,6 +145,34 @@ int launch_pad_rois(frcnn_handle* h, cudaStream_t stream, const int16_t* rois, c
   return FRCNN_OK;
 }
 
+// Mini-batch gather of DetTrainingManager.get_training_input (det_util.py:119-125: rois[sampled_idxs],
+// y_class_num[sampled_idxs], y_transform[sampled_idxs]) for a batch of images: one CTA per (sample, image) copies the
+// three labelled rows index[img][s] points at; index -1 (image without eligible RoI) writes zero rows.
+__global__ void __launch_bounds__(128)
+gather_det_samples_kernel(const unsigned long long* __restrict__ rois, const int* __restrict__ y_cls,
+                          const float* __restrict__ y_tr, const int* __restrict__ index, int n_max, int k, int t,
+                          int n_samples, unsigned long long* __restrict__ out_rois, int* __restrict__ out_cls,
+                          float* __restrict__ out_tr) {
+  const int s = blockIdx.x, img = blockIdx.y;
+  const int src = __ldg(index + (size_t)img * n_samples + s);
+  const bool live = src >= 0 && src < n_max;
+  const size_t in_row = (size_t)img * n_max + (live ? src : 0), out_row = (size_t)img * n_samples + s;
+  if (threadIdx.x == 0) out_rois[out_row] = live ? __ldg(rois + in_row) : 0ull;
+  for (int i = threadIdx.x; i < k; i += 128) out_cls[out_row * k + i] = live ? __ldg(y_cls + in_row * k + i) : 0;
+  for (int i = threadIdx.x; i < t; i += 128) out_tr[out_row * t + i] = live ? __ldg(y_tr + in_row * t + i) : 0.f;
+}
+
+int launch_gather_det_samples(frcnn_handle* h, cudaStream_t stream, const int16_t* rois, const int32_t* y_cls,
+                              const float* y_tr, const int32_t* index, int n_max, int k, int t, int n_samples, int batch,
+                              int16_t* out_rois, int32_t* out_cls, float* out_tr) {
+  dim3 grid(n_samples, batch);
+  gather_det_samples_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const unsigned long long*>(rois), y_cls, y_tr, index,
+                                                     n_max, k, t, n_samples,
+                                                     reinterpret_cast<unsigned long long*>(out_rois), out_cls, out_tr);
+  FRCNN_LAUNCH_CHECK(h, "gather_det_samples_kernel");
+  return FRCNN_OK;
+}
+
 int launch_cross_ious(frcnn_handle* h, cudaStream_t stream, const void* boxes, int dtype, int n, const float* gt,
                       int g, float* iou) {
   const size_t total = (size_t)n * g;

@@ -30,6 +30,8 @@ int launch_cross_ious(frcnn_handle*, cudaStream_t, const void*, int, int, const 
 int launch_box_transform(frcnn_handle*, cudaStream_t, float*, const float*, int, int, int, int);
 int launch_anchor_grid(frcnn_handle*, cudaStream_t, const AnchorTable&, int, int, int, int, float*);
 int launch_valid_boxes(frcnn_handle*, cudaStream_t, const float*, int, int32_t*, int32_t*);
+int launch_gather_det_samples(frcnn_handle*, cudaStream_t, const int16_t*, const int32_t*, const float*, const int32_t*,
+                              int, int, int, int, int, int16_t*, int32_t*, float*);
 int launch_pad_rois(frcnn_handle*, cudaStream_t, const int16_t*, const int32_t*, int, int, int, int, int16_t*,
                     int32_t*);
 
@@ -365,6 +367,17 @@ int frcnn_pad_rois(frcnn_handle* h, void* stream, const int16_t* rois, const int
   FRCNN_REQUIRE(h, n_max > 0 && group > 0 && batch > 0 && batch <= 65535, "pad_rois: bad size");
   FRCNN_REQUIRE(h, m_out >= (n_max + group - 1) / group * group, "pad_rois: m_out smaller than n_max rounded up to the group size");
   return launch_pad_rois(h, st, rois, count, n_max, group, m_out, batch, out, out_rows);
+}
+
+int frcnn_gather_det_samples(frcnn_handle* h, void* stream, const int16_t* rois, const int32_t* y_cls, const float* y_tr,
+                             const int32_t* index, int n_max, int n_classes, int n_samples, int batch,
+                             int16_t* out_rois, int32_t* out_cls, float* out_tr) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, rois && y_cls && y_tr && index && out_rois && out_cls && out_tr, "gather_det_samples: null pointer");
+  FRCNN_REQUIRE(h, n_max > 0 && n_classes >= 2 && n_samples > 0 && batch > 0 && batch <= 65535,
+                "gather_det_samples: bad size");
+  return launch_gather_det_samples(h, st, rois, y_cls, y_tr, index, n_max, n_classes, 8 * (n_classes - 1), n_samples,
+                                   batch, out_rois, out_cls, out_tr);
 }
 
 int frcnn_rpn_losses(frcnn_handle* h, void* stream, const uint8_t* can_use, const uint8_t* is_pos, const float* bbreg,

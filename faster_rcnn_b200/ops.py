@@ -232,6 +232,23 @@ def det_postprocess(rois, out_cls, out_reg, resize_ratio, bg_index, stride=16, d
     return boxes, probs, cls, count
 
 
+def gather_det_samples(rois, y_cls, y_tr, index):
+    """det_util.py:119-125 batched: rows `index` (B,S) i32 of label_rois's outputs -> rois (B,S,4) i16,
+    y_class_num (B,S,K) i32, y_transform (B,S,8(K-1)) f32; index -1 gives zero rows."""
+    rois, y_cls = _chk(rois, torch.int16, "rois", 3), _chk(y_cls, torch.int32, "y_cls", 3)
+    y_tr, index = _chk(y_tr, torch.float32, "y_tr", 3), _chk(index, torch.int32, "index", 2)
+    ctx = get_context(rois.device)
+    b, n_max, _ = rois.shape
+    k, s = y_cls.shape[2], index.shape[1]
+    if y_cls.shape != (b, n_max, k) or y_tr.shape != (b, n_max, 8 * (k - 1)) or index.shape[0] != b:
+        raise ValueError("gather_det_samples: inconsistent shapes")
+    out_rois, out_cls = ctx.empty((b, s, 4), torch.int16), ctx.empty((b, s, k), torch.int32)
+    out_tr = ctx.empty((b, s, 8 * (k - 1)), torch.float32)
+    ctx.call("frcnn_gather_det_samples", ptr(rois), ptr(y_cls), ptr(y_tr), ptr(index), n_max, k, s, b, ptr(out_rois),
+             ptr(out_cls), ptr(out_tr))
+    return out_rois, out_cls, out_tr
+
+
 def cross_ious(boxes, gt):
     """util.cross_ious (util.py:146-177).  boxes (N,4) i16 or f32, gt (G,4) f32 -> (N,G) f32."""
     if boxes.dtype not in (torch.int16, torch.float32):

@@ -212,3 +212,61 @@ class DetectionPipeline(ProposalRoiPipeline):
         names = {v: k for k, v in self.class_mapping.items()}
         return [[{'bbox': boxes[b, i].astype(np.int64), 'cls_name': names[int(dcls[b, i])], 'prob': probs[b, i]}
                  for i in range(int(count[b]))] for b in range(len(count))]
+
+
+class DetTrainingPipeline:
+    """Detector-training inputs of `DetTrainingManager.get_training_input` (det_util.py:63-133) for a BATCH of images,
+    device-resident:
+
+        RPN head outputs -> proposals (top-k 12000, NMS 0.7 -> 2000) -> RoI x GT labelling (eligible >= 0.1, positive
+        >= 0.5, one-hot classes, class-specific regression targets) -> 64-RoI mini-batch (<= 25 % positives)
+        [-> RoI layer on the sampled RoIs]
+
+    Only the mini-batch draw runs on the host: it replays `det_util._get_det_samples` with numpy's legacy global RNG,
+    image by image in batch order, so the result equals calling the reference-shaped manager on each image in turn
+    (one D2H of the positive flags and counts, one H2D of the B x 64 sample rows).  An image without an eligible RoI
+    (the reference returns 4 x None) gets zero rows and `has_rois[b] = False`."""
+
+    def __init__(self, class_mapping, anchor_dims=DEFAULT_ANCHORS, stride=16, num_rois=64, pre_nms_topk=12000,
+                 nms_thresh=0.7, max_boxes=2000, pool_size=7, mode="resize", device=None):
+        if class_mapping['bg'] != len(class_mapping) - 1:
+            raise NotImplementedError("'bg' must be the last class index (the reference assumes it too: det_util.py:120)")
+        self.class_mapping, self.anchor_dims = class_mapping, np.asarray(anchor_dims)
+        self.stride, self.num_rois, self.k, self.thresh, self.max_boxes = stride, num_rois, pre_nms_topk, nms_thresh, max_boxes
+        self.pool_size, self.mode = pool_size, mode
+        self.ctx = get_context(device)
+
+    def ground_truth(self, images):
+        """list of images -> (gt (B,Gmax,4) f64 feature units, gt_cls (B,Gmax) i32, n_gt (B,) i32) on the device."""
+        from .det_util import _gt_feature_boxes
+        per = [_gt_feature_boxes(img, self.class_mapping, self.stride) for img in images]
+        g_max = max(len(g) for g, _ in per)
+        gt = np.zeros((len(per), g_max, 4), np.float64)
+        gt_cls = np.zeros((len(per), g_max), np.int32)
+        for b, (g, c) in enumerate(per):
+            gt[b, :len(g)], gt_cls[b, :len(c)] = g, c
+        n_gt = np.array([len(g) for g, _ in per], np.int32)
+        return self.ctx.to_device(gt), self.ctx.to_device(gt_cls), self.ctx.to_device(n_gt)
+
+    def targets(self, cls, regr, gt, gt_cls, n_gt):
+        """CUDA tensors in -> (rois (B,S,4) i16, y_class_num (B,S,K) i32, y_transform (B,S,8(K-1)) f32) on the device and
+        has_rois (B,) bool on the host."""
+        from .det_util import _get_det_samples
+        rois, _, count = ops.proposals(regr, cls, self.anchor_dims, self.stride, self.k, self.thresh, self.max_boxes)
+        l_rois, y_cls, y_tr, _, m = ops.label_rois(rois, gt, gt_cls, n_gt, len(self.class_mapping), n_roi=count)
+        found = self.ctx.to_host((y_cls[:, :, -1] == 0).to(torch.uint8))          # positives = not background
+        m_host = self.ctx.to_host(m)
+        index = np.full((len(m_host), self.num_rois), -1, np.int32)
+        for b, mb in enumerate(m_host.tolist()):                                   # RNG draws in image order
+            if mb > 0:
+                index[b] = _get_det_samples(found[b, :mb] == 1, self.num_rois)
+        out = ops.gather_det_samples(l_rois, y_cls, y_tr, self.ctx.to_device(index))
+        return out + (m_host > 0,)
+
+    def __call__(self, cls, regr, feat, images):
+        """Host or device arrays + the images' ground truth -> (rois, y_class_num, y_transform, pooled, has_rois):
+        the detector's training inputs and the RoI layer's output on the sampled RoIs (CUDA tensors)."""
+        dev_in = [x if (isinstance(x, torch.Tensor) and x.is_cuda) else self.ctx.to_device(x, np.float32) for x in (cls, regr, feat)]
+        rois, y_cls, y_tr, has = self.targets(dev_in[0], dev_in[1], *self.ground_truth(images))
+        pooled = ops.roi_forward(dev_in[2], rois, self.pool_size, self.mode)
+        return rois, y_cls, y_tr, pooled, has

@@ -229,6 +229,15 @@ FRCNN_API int frcnn_valid_boxes(frcnn_handle* h, void* stream, const float* boxe
 FRCNN_API int frcnn_pad_rois(frcnn_handle* h, void* stream, const int16_t* rois, const int32_t* count,
                              int n_max, int group, int m_out, int batch, int16_t* out, int32_t* out_rows);
 
+/* Mini-batch gather of DetTrainingManager.get_training_input (det_util.py:119-125) for a batch of images:
+ * rois [batch,n_max,4] i16, y_cls [batch,n_max,K] i32, y_tr [batch,n_max,8(K-1)] f32 are frcnn_label_rois's
+ * outputs, index [batch,n_samples] i32 the host-drawn sample rows (det_util._get_det_samples, numpy's legacy RNG);
+ * index -1 (image without an eligible RoI: the reference returns 4 x None) yields zero rows.
+ * out_rois [batch,n_samples,4], out_cls [batch,n_samples,K], out_tr [batch,n_samples,8(K-1)]. */
+FRCNN_API int frcnn_gather_det_samples(frcnn_handle* h, void* stream, const int16_t* rois, const int32_t* y_cls,
+                                       const float* y_tr, const int32_t* index, int n_max, int n_classes,
+                                       int n_samples, int batch, int16_t* out_rois, int32_t* out_cls, float* out_tr);
+
 /* ---- masked losses fused with the path's own targets (widening row)
  * Replaces loss_functions.py:15-48 (cls_loss_rpn, bbreg_loss_rpn) and :51-76 (bbreg_loss_det,
  * cls_loss_det), i.e. the Keras-backend expressions with binary_crossentropy / categorical_crossentropy

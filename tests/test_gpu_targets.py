@@ -9,6 +9,7 @@ import pytest
 
 from helpers import FakeImage, FakeRpn, dev, golden, host
 from oracle import frcnn_oracle as O
+from oracle import roi_oracle as R
 
 pytestmark = pytest.mark.gpu
 
@@ -333,3 +334,39 @@ def test_util_dropin_vs_golden():
     want = O.decode_boxes(boxes.copy(), deltas)
     got = util.transform_np_inplace(boxes, deltas)
     assert got is boxes and np.sum(np.any(got != want, axis=1)) <= 1
+
+
+def test_det_training_pipeline_equals_per_image_manager():
+    """pipeline.DetTrainingPipeline (batched, device-resident) == DetTrainingManager.get_training_input called on each
+    image in turn with the same numpy RNG stream, incl. an image whose GT overlaps no proposal (4 x None)."""
+    import torch
+    from faster_rcnn_b200 import det_util, synth
+    from faster_rcnn_b200.pipeline import DetTrainingPipeline
+    dims = O.anchor_table([128, 256, 512])
+    mapping = synth.VOC_CLASS_MAPPING
+    rows, cols, ch, b = 19, 25, 32, 4
+    heads = [synth.rpn_outputs(rows, cols, 9, 70 + i, clustered=True) for i in range(b)]
+    gts = [synth.gt_boxes(6, 400, 300, 80 + i) for i in range(b)]
+    gts[2] = [("cat", 1, 1, 3, 3)]                                   # 2x2 px object: IoU < 0.1 with every proposal
+    images = [FakeImage("im%d" % i, 400, 300, g, data=np.zeros((2, 2, 3), np.float32)) for i, g in enumerate(gts)]
+    feat = np.random.default_rng(5).standard_normal((b, rows, cols, ch), dtype=np.float32)
+
+    np.random.seed(1337)
+    want = []
+    for (cls, regr), img in zip(heads, images):
+        mgr = det_util.DetTrainingManager(FakeRpn(cls, regr), mapping, lambda d: d, anchor_dims=dims)
+        want.append(mgr.get_training_input(img))
+    assert want[2] == (None, None, None, None) and want[0][1] is not None
+
+    pipe = DetTrainingPipeline(mapping, dims)
+    np.random.seed(1337)
+    rois, y_cls, y_tr, pooled, has = pipe(np.concatenate([h[0] for h in heads]), np.concatenate([h[1] for h in heads]), feat, images)
+    assert has.tolist() == [True, True, False, True]
+    rois, y_cls, y_tr = host(rois), host(y_cls), host(y_tr)
+    for i in range(b):
+        if want[i][1] is None:
+            assert not rois[i].any() and not y_cls[i].any() and not y_tr[i].any()
+            continue
+        assert np.array_equal(rois[i], want[i][1][0]) and np.array_equal(y_cls[i], want[i][2][0])
+        assert np.array_equal(y_tr[i], want[i][3][0])
+        assert np.array_equal(host(pooled)[i], R.roi_resize_fwd(feat[i], rois[i], 7))
