@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Randomised GPU-vs-oracle parity sweep (not part of pytest; run on the GPU box):
+
+    python benchmarks/fuzz_parity.py [--cases 300] [--seed 0]
+
+Draws shapes / thresholds / limits the fixed test parametrisations do not cover (NMS stopping inside a tile, 1-box
+inputs, heavy ties, thresholds at 0 and 1, odd channel counts and pool sizes, ragged batches) and compares every
+result bit for bit with the oracle (resize-mode RoI backward: 1e-5 relative).  Prints one JSON summary line."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from faster_rcnn_b200 import ops, synth          # noqa: E402
+from oracle import frcnn_oracle as O             # noqa: E402
+from oracle import roi_oracle as R               # noqa: E402
+
+
+def dev(x, dtype=None):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=dtype)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def case_nms(rng):
+    n = int(rng.choice([1, 2, 63, 64, 65, 200, 1000, 3000]))
+    span = int(rng.choice([20, 60, 200]))
+    x1, y1 = rng.integers(0, span, n), rng.integers(0, span, n)
+    boxes = np.stack([x1, y1, x1 + rng.integers(0, 40, n), y1 + rng.integers(0, 40, n)], 1).astype(np.int16)
+    if rng.random() < 0.3:                                      # heavy duplicates -> many exact-threshold / IoU 1 pairs
+        boxes = boxes[rng.integers(0, max(1, n // 4), n)]
+    probs = rng.permutation(n).astype(np.float32) / n if rng.random() < 0.7 else rng.integers(0, 5, n).astype(np.float32)
+    thresh = float(rng.choice([0.0, 0.3, 0.5, 0.7, 0.999, 1.0]))
+    max_boxes = int(rng.choice([1, 2, 7, 64, 65, 300, 2000]))
+    pick = O.greedy_nms(boxes, probs, thresh, max_boxes)
+    ki, kc, kb, ks = ops.nms_i16(dev(boxes[None]), dev(probs[None]), None, thresh, max_boxes)
+    m = int(host(kc)[0])
+    ok = m == len(pick) and np.array_equal(host(ki)[0, :m], pick) and np.array_equal(host(kb)[0, :m], boxes[pick])
+    return ok, dict(kind="nms", n=n, thresh=thresh, max_boxes=max_boxes)
+
+
+def case_proposals(rng):
+    rows, cols = int(rng.integers(1, 40)), int(rng.integers(1, 70))
+    scales = [128, 256, 512] if rng.random() < 0.6 else [16, 32, 64, 128, 256, 512]
+    dims = O.anchor_table(scales)
+    cls, regr = synth.rpn_outputs(rows, cols, len(dims), int(rng.integers(1 << 30)), clustered=bool(rng.random() < 0.5))
+    k = int(rng.choice([1, 50, 1024, 2049, 8000, 12000]))
+    max_boxes = int(rng.choice([1, 10, 300, 2000]))
+    dense = host(ops.decode_topk(dev(regr), dev(cls), dims, 16, k, want_dense=True)[4])[0]
+    wb, wp, _ = O.topk_proposals(dense.copy(), cls.reshape(-1), k)
+    pick = O.greedy_nms(wb, wp, 0.7, max_boxes) if len(wb) else np.zeros(0, np.int64)
+    rois, scores, count = ops.proposals(dev(regr), dev(cls), dims, 16, k, 0.7, max_boxes)
+    m = int(host(count)[0])
+    ok = m == len(pick) and np.array_equal(host(rois)[0, :m], wb[pick]) and np.array_equal(host(scores)[0, :m], wp[pick])
+    return ok, dict(kind="proposals", rows=rows, cols=cols, a=len(dims), k=k, max_boxes=max_boxes)
+
+
+def case_roi(rng):
+    h, w = int(rng.integers(1, 40)), int(rng.integers(1, 64))
+    c = int(rng.choice([4, 20, 64, 128, 260, 384, 512, 1024]))
+    n, b = int(rng.choice([1, 3, 33, 64, 300])), int(rng.choice([1, 2, 5]))
+    pool = int(rng.choice([1, 3, 7, 7, 7, 9, 14]))
+    if n * b * pool * pool * c > 40e6:
+        n = max(1, int(40e6 // (b * pool * pool * c)))
+    feat = rng.standard_normal((b, h, w, c), dtype=np.float32)
+    if rng.random() < 0.5:
+        feat = np.round(feat)                                   # ties for the max mode
+    x1, y1 = rng.integers(0, w, (b, n)), rng.integers(0, h, (b, n))
+    rois = np.stack([x1, y1, np.minimum(w, x1 + 1 + rng.integers(0, w, (b, n))), np.minimum(h, y1 + 1 + rng.integers(0, h, (b, n)))], 2).astype(np.int16)
+    gout = rng.standard_normal((b, n, pool, pool, c), dtype=np.float32)
+    out = host(ops.roi_forward(dev(feat), dev(rois), pool, "resize"))
+    g = host(ops.roi_backward(dev(gout), dev(rois), (b, h, w, c), "resize"))
+    mo, ma = ops.roi_forward(dev(feat), dev(rois), pool, "max")
+    gm = host(ops.roi_backward(dev(gout), dev(rois), (b, h, w, c), "max", argmax=ma))
+    ok = True
+    for i in range(b):
+        ok &= np.array_equal(out[i], R.roi_resize_fwd(feat[i], rois[i], pool))
+        want = R.roi_resize_bwd(gout[i], rois[i], (h, w, c))
+        ok &= bool(np.abs(g[i] - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30))
+        wo, wa = R.roi_max_fwd(feat[i], rois[i], pool)
+        ok &= np.array_equal(host(mo)[i], wo) and np.array_equal(host(ma)[i], wa)
+        ok &= np.array_equal(gm[i], R.roi_max_bwd(gout[i], wa, (h, w, c)))
+    return bool(ok), dict(kind="roi", h=h, w=w, c=c, n=n, b=b, pool=pool)
+
+
+def case_labels(rng):
+    rows, cols = int(rng.integers(2, 40)), int(rng.integers(2, 64))
+    dims = O.anchor_table([128, 256, 512])
+    W, H = cols * 16, rows * 16
+    g = int(rng.choice([1, 2, 7, 50]))
+    gts = np.array([x[1:] for x in synth.gt_boxes(g, max(W, 64), max(H, 64), int(rng.integers(1 << 30)))], np.float32)
+    cu, ip, bb, _ = ops.label_anchors(dev(gts[None]), dev(np.array([g], np.int32)), dev(np.array([[W, H]], np.int32)), rows, cols, dims, 16)
+    wc, wp, wb = O.label_anchors(W, H, gts, rows, cols, dims, 16)
+    ok = np.array_equal(host(cu)[0] == 1, wc) and np.array_equal(host(ip)[0] == 1, wp)
+    diff = np.abs(host(bb)[0] - wb)
+    ok &= bool(np.all(diff <= 2e-6 * np.maximum(np.abs(wb), 1.0)))       # log() in the targets: <= 1 ulp after the f32 store
+    return bool(ok), dict(kind="labels", rows=rows, cols=cols, g=g)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=300)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    kinds = [case_nms, case_proposals, case_roi, case_labels]
+    counts, failures = {}, []
+    for i in range(args.cases):
+        fn = kinds[i % len(kinds)]
+        ok, info = fn(rng)
+        counts[info["kind"]] = counts.get(info["kind"], 0) + 1
+        if not ok:
+            failures.append(info)
+            print("FAIL", json.dumps(info), flush=True)
+    print(json.dumps({"cases": args.cases, "seed": args.seed, "per_kind": counts, "failures": len(failures)}))
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()
