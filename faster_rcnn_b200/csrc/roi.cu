@@ -52,8 +52,43 @@ __device__ __forceinline__ Tap axis_tap(int i, float scale, int in_size) {
   return t;
 }
 
+// Blackwell packed fp32 (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2): two IEEE-rounded float32 results per
+// instruction on an aligned register pair, i.e. half the issue slots for the same arithmetic.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// a + (b - a) * t with three roundings per element like numpy / TF's CPU kernel.  The subtraction and the product are
+// packed; the final addition stays scalar because ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (a
+// single rounding) even with -fmad=false, which would break the bit-exact forward.  8 instead of 12 instructions.
 __device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
-  return make_float4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t);
+  const unsigned long long tt = pack2(t, t);
+  const unsigned long long p0 = mul2(sub2(pack2(b.x, b.y), pack2(a.x, a.y)), tt);
+  const unsigned long long p1 = mul2(sub2(pack2(b.z, b.w), pack2(a.z, a.w)), tt);
+  float px, py, pz, pw;
+  unpack2(p0, px, py);
+  unpack2(p1, pz, pw);
+  return make_float4(__fadd_rn(a.x, px), __fadd_rn(a.y, py), __fadd_rn(a.z, pz), __fadd_rn(a.w, pw));
 }
 
 __device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -260,15 +295,16 @@ __device__ __forceinline__ void cell_accumulate(int yc, int xc, float wy1, float
                                                 float4 (&acc)[CPB]) {
   const float wy0 = 1.0f - wy1, wx0 = 1.0f - wx1;
   // Taps in the order TL, TR, BL, BR.  The four conditions are warp-uniform and sit outside the channel
-  // loop (4 branches per bin).  The tap weight wy*wx is formed once per bin and applied with one FMA per
-  // element: resize-mode gradients are a tolerance comparison anyway (fixed but different summation order
+  // loop (4 branches per bin).  The tap weight wy*wx is formed once per bin and applied with one (packed, FFMA2) FMA per
+  // element pair: resize-mode gradients are a tolerance comparison anyway (fixed but different summation order
   // than TF's slice-grad + AddN; TF's own GPU kernel uses atomics), and this cuts the FP instruction count 3x.
 #define FRCNN_CELL_ACCUM(WY, WX)                                                              \
   {                                                                                            \
     const float wgt = __fmul_rn(WY, WX);                                                       \
+    const unsigned long long ww = pack2(wgt, wgt);                                             \
     _Pragma("unroll") for (int j = 0; j < CPB; ++j) {                                          \
-      acc[j].x = __fmaf_rn(g[j].x, wgt, acc[j].x); acc[j].y = __fmaf_rn(g[j].y, wgt, acc[j].y); \
-      acc[j].z = __fmaf_rn(g[j].z, wgt, acc[j].z); acc[j].w = __fmaf_rn(g[j].w, wgt, acc[j].w); \
+      unpack2(fma2(pack2(g[j].x, g[j].y), ww, pack2(acc[j].x, acc[j].y)), acc[j].x, acc[j].y);  \
+      unpack2(fma2(pack2(g[j].z, g[j].w), ww, pack2(acc[j].z, acc[j].w)), acc[j].z, acc[j].w);  \
     }                                                                                          \
   }
   if ((yc & 1) && (xc & 1)) FRCNN_CELL_ACCUM(wy0, wx0)
@@ -289,7 +325,7 @@ __device__ __forceinline__ void cell_accumulate(int yc, int xc, float wy1, float
 // measured too: 0.31 / 0.24 ms -- beyond RS = 4 the launch is bound by resident warps x bytes in flight, not by the
 // longest chain).  The summation order is still fixed (deterministic), just not the RS = 1 order.
 template <int CPB, bool FULL, int G, int RS>
-__global__ void __launch_bounds__(CW_WARPS * 32)
+__global__ void __launch_bounds__(CW_WARPS * 32, (RS == 1 && CPB == 8) ? 3 : 0)      // 3 CTAs per SM need <= 80 registers
 roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restrict__ crops,
                            const int4* __restrict__ taps, int H, int W, int C, int N, int P,
                            float* __restrict__ gfeat) {
