@@ -215,3 +215,33 @@ def test_voc_eval_live(ref, tmp_path):
     r, p, a = E.voc_match([l[0] for l in lines], conf, np.array([l[1] for l in lines]), gt)
     assert np.array_equal(r, rec) and np.array_equal(p, prec) and a == ap and ap > 0.05
     assert E.voc_ap(rec, prec, False) == ref_eval.voc_ap(rec, prec, False)
+
+
+def test_shapes_value_objects_match_the_reference(ref):
+    """faster_rcnn_b200.shapes (Box / GroundTruthBox / Image geometry: dims, centres, resize, resize_within_bounds,
+    horizontal_flip, cache_key) against the reference's shapes.py on the VOC 000005 boxes and synthetic ones."""
+    from faster_rcnn_b200 import shapes as M
+    S = ref.shapes
+    gts = [("chair", 262, 210, 323, 338), ("chair", 164, 263, 252, 371), ("chair", 4, 243, 66, 373)] + synth.gt_boxes(9, 500, 375, 4)
+    mine = M.Image("000005", 500, 375, [M.GroundTruthBox(c, False, M.Box(*b)) for c, *b in gts])
+    theirs = _ref_image(ref, "000005", 500, 375, gts)
+
+    def same(a, b):
+        assert (a.width, a.height, a.cache_key, a.num_gt_boxes) == (b.width, b.height, b.cache_key, b.num_gt_boxes)
+        for ga, gb in zip(a.gt_boxes, b.gt_boxes):
+            assert ga.obj_cls == gb.obj_cls and ga.difficult == gb.difficult
+            for attr in ("corners", "corner_dims", "center_dims"):
+                assert np.array_equal(getattr(ga, attr), getattr(gb, attr))
+            assert (ga.x1, ga.y1, ga.x2, ga.y2, ga.width, ga.height, ga.x_center, ga.y_center) == \
+                   (gb.x1, gb.y1, gb.x2, gb.y2, gb.width, gb.height, gb.x_center, gb.y_center)
+
+    same(mine, theirs)
+    (m2, r_m), (t2, r_t) = mine.resize_within_bounds(600, 1000), theirs.resize_within_bounds(600, 1000)
+    assert r_m == r_t == 1.6
+    same(m2, t2)
+    same(m2.horizontal_flip(), t2.horizontal_flip())
+    same(m2.horizontal_flip().horizontal_flip(), t2.horizontal_flip().horizontal_flip())
+    same(mine.resize(0.37), theirs.resize(0.37))
+    for args in ((456, 264, 128, 128), (8, 8, 91, 181), (0, 0, 5, 11)):
+        assert np.array_equal(M.Box.from_center_dims_int(*args).corners, S.Box.from_center_dims_int(*args).corners)
+    assert np.array_equal(M.Box.from_corners([1, 2, 3, 4]).corners, S.Box.from_corners([1, 2, 3, 4]).corners)
