@@ -285,7 +285,10 @@ __global__ void roi_fwd_scalar_kernel(const float* __restrict__ feat, int H, int
 // dY rows are shared by the <= 4 neighbouring cells they touch; neighbouring cells sit in the
 // same CTA (x direction) or the same wave (y direction), so the re-reads hit L1 / L2, not DRAM.
 // ---------------------------------------------------------------------------------------
-constexpr int CW_WARPS = 8;
+// 4-warp CTAs: a CTA slot is only recycled when its slowest warp is done (cells differ in the number of RoIs that
+// cover them), and with 8 warps per CTA only 18 of the 24 resident warp slots were busy (ncu); 4 and 2 warps per CTA
+// both measured 1.06 ms against 1.13-1.20 ms (resize), 2.47 against 2.62-2.69 ms (max) at C1 x 64 images.
+constexpr int CW_WARPS = 4;
 // Measured and rejected (profiles/): queueing the contributions per warp in shared memory and streaming
 // them with a two-deep software pipeline (2.1 ms vs 1.34 ms at C1 x 64 images): separating the integer
 // "collect" phase from the load phase removes the overlap that independent warps get for free.
@@ -324,15 +327,15 @@ __device__ __forceinline__ void cell_accumulate(int yc, int xc, float wy1, float
 // split shortens that chain RS-fold (0.335 -> 0.246 ms at 2000 RoIs x 1 image; RS = 2 / 8 and 512-channel warps were
 // measured too: 0.31 / 0.24 ms -- beyond RS = 4 the launch is bound by resident warps x bytes in flight, not by the
 // longest chain).  The summation order is still fixed (deterministic), just not the RS = 1 order.
-template <int CPB, bool FULL, int G, int RS>
-__global__ void __launch_bounds__(CW_WARPS * 32, (RS == 1 && CPB == 8) ? 3 : 0)      // 3 CTAs per SM need <= 80 registers
+template <int CPB, bool FULL, int G, int RS, int WARPS = (RS > 1 ? RS : CW_WARPS)>
+__global__ void __launch_bounds__(WARPS * 32, (RS == 1 && CPB == 8) ? 768 / (WARPS * 32) : 0)      // 24 warps per SM need <= 80 registers
 roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restrict__ crops,
                            const int4* __restrict__ taps, int H, int W, int C, int N, int P,
                            float* __restrict__ gfeat) {
-  __shared__ float4 s_part[RS > 1 ? CW_WARPS * CPB * 32 : 1];
+  __shared__ float4 s_part[RS > 1 ? WARPS * CPB * 32 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int part = warp % RS;
-  const int cell_raw = blockIdx.x * (CW_WARPS / RS) + warp / RS;
+  const int cell_raw = blockIdx.x * (WARPS / RS) + warp / RS;
   const bool live = cell_raw < H * W;
   if (RS == 1 && !live) return;                     // warp-uniform; the RS = 1 kernel has no block-level barrier
   const int cell = live ? cell_raw : 0;
@@ -450,7 +453,7 @@ roi_bwd_resize_cell_kernel(const float* __restrict__ gout, const int4* __restric
 // warps buy throughput: the 512-channel variant used for small launches is capped at 64 registers (4 CTAs per SM;
 // 2000 RoIs x 1 image: 0.54 -> 0.36 ms).  The same cap on the 1024-channel variant spills and was 5 % slower at 8 images.
 template <int CPB, bool FULL, int G>
-__global__ void __launch_bounds__(CW_WARPS * 32, CPB == 8 ? 0 : 4)
+__global__ void __launch_bounds__(CW_WARPS * 32, CPB == 8 ? 0 : 1024 / (CW_WARPS * 32))
 roi_bwd_max_cell_kernel(const float* __restrict__ gout, const int* __restrict__ argmax,
                         const int4* __restrict__ crops, const int4* __restrict__ taps, int H, int W, int C, int N,
                         int P, float* __restrict__ gfeat) {
@@ -682,14 +685,14 @@ int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
     const long long cell_warps = (long long)H * W * batch * ((blocks128 + cpb - 1) / cpb);
     const bool split = mode == FRCNN_ROI_RESIZE && P <= 8 && cell_warps < 4LL * h->sm_count * 24 && N >= 256;
     if (!split && cpb == 8 && (long long)H * W * batch < 2LL * h->sm_count * 32) cpb = 4;
-    const int cells_per_cta = split ? CW_WARPS / 4 : CW_WARPS;
+    const int cells_per_cta = split ? 1 : CW_WARPS;        // split: one cell per 4-warp CTA
     dim3 grid((H * W + cells_per_cta - 1) / cells_per_cta, (blocks128 + cpb - 1) / cpb, batch);
 #define FRCNN_LAUNCH_CELL(CPB)                                                                                      \
   if (mode == FRCNN_ROI_RESIZE) {                                                                                   \
     if (split && C % (CPB * 128) == 0)                                                                              \
-      roi_bwd_resize_cell_kernel<CPB, true, 8, 4><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+      roi_bwd_resize_cell_kernel<CPB, true, 8, 4><<<grid, 4 * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
     else if (split)                                                                                                 \
-      roi_bwd_resize_cell_kernel<CPB, false, 8, 4><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
+      roi_bwd_resize_cell_kernel<CPB, false, 8, 4><<<grid, 4 * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat); \
     else if (C % (CPB * 128) == 0 && P <= 8)                                                                        \
       roi_bwd_resize_cell_kernel<CPB, true, 8, 1><<<grid, CW_WARPS * 32, 0, stream>>>(gout, crops, taps, H, W, C, N, P, gfeat);  \
     else if (P <= 8)                                                                                                \
