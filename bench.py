@@ -329,6 +329,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "inputs larger than L2 (%.0f MB of features + %.0f MB of pooled output per step vs 126 MB L2)"
                              % (batch * ROWS * COLS * CHANNELS * 4 / 1e6, batch * PADDED * POOL * POOL * CHANNELS * 4 / 1e6),
                        "rois_per_image": int(count0[0]),
+                       "timing": "CUDA events around K back-to-back steps after W warm-up steps; runs of hundreds of steps "
+                                 "reach the 1000 W power cap (clocks.reasons: sw_power_cap) and measure 6-8 % lower",
                        "host_affinity": ("rank 0 bound to %d GPU-local cores" % len(numa_cores)) if numa_cores else "unbound"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
