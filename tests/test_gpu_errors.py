@@ -50,3 +50,31 @@ def test_python_layer_type_checks():
         det_util.nms(np.zeros((3, 4), np.int16), np.array([0.1, 0.2, 1 / 3], dtype=np.float64))  # not float32-representable
     with pytest.raises(ValueError):
         det_util.nms(np.zeros((5000, 4), np.float64), np.arange(5000, dtype=np.float32))         # float path capacity
+
+
+def test_new_entry_points_reject_bad_arguments():
+    import torch
+    from faster_rcnn_b200 import _lib, ops, synth
+    from faster_rcnn_b200.pipeline import DetTrainingPipeline, ProposalRoiPipeline
+    from faster_rcnn_b200.runtime import get_context, ptr
+    ctx = get_context()
+    rois, y_cls = dev(np.zeros((2, 5, 4), np.int16)), dev(np.zeros((2, 5, 21), np.int32))
+    y_tr, index = dev(np.zeros((2, 5, 160), np.float32)), dev(np.zeros((2, 3), np.int32))
+    with pytest.raises(ValueError):
+        ops.gather_det_samples(rois, y_cls, y_tr[:, :, :100].contiguous(), index)               # 8(K-1) columns expected
+    with pytest.raises(_lib.FrcnnError) as e:                                                      # NULL output through the raw ABI
+        ctx.call("frcnn_gather_det_samples", ptr(rois), ptr(y_cls), ptr(y_tr), ptr(index), 5, 21, 3, 2, None, None, None)
+    assert e.value.code == _lib.ERR_INVALID and "gather_det_samples" in str(e.value)
+    # out-of-range and -1 sample rows give zero rows, never an out-of-bounds read
+    out = ops.gather_det_samples(rois + 7, y_cls + 1, y_tr + 1.0, dev(np.array([[0, -1, 99], [4, 5, 2]], np.int32)))
+    got = [t.cpu().numpy() for t in out]
+    assert got[0][0, 0].tolist() == [7, 7, 7, 7] and not got[0][0, 1:].any() and not got[1][1, 1].any() and got[2][1, 2, 0] == 1.0
+    with pytest.raises(NotImplementedError):
+        DetTrainingPipeline({'bg': 0, 'cat': 1})                                                  # 'bg' must be the last class
+    # a captured graph keeps its shapes: other shapes must be captured separately
+    dims = np.array([[8, 8], [16, 16]]) * 16
+    pipe = ProposalRoiPipeline(dims, 16, 50, 0.7, 10, 8, 7, "resize")
+    cls, regr = synth.rpn_outputs(6, 7, 2, 1)
+    run = pipe.capture(dev(cls), dev(regr), torch.randn((1, 6, 7, 16), device="cuda"))
+    with pytest.raises(RuntimeError):
+        run(feat=torch.randn((1, 6, 7, 32), device="cuda"))
