@@ -21,6 +21,8 @@
 // through to the IEEE float64 division, so the decision is identical to numpy's.
 #include <cooperative_groups.h>
 
+#include <math.h>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -69,6 +71,22 @@ __device__ __forceinline__ int screen_i16(int ax1, int ay1, int ax2, int ay2, in
   return (d > band) ? 1 : ((d < -band && uni > 0) ? 0 : 2);
 }
 
+// Thresholds that are a ratio of small integers (0.7 = 7/10 as a double: the RPN's value) need no fixed point and no
+// band: with t_d = RN(p/q), RN(inter/union) <= t_d  <=>  inter*q <= p*union, exactly.  (If inter/union <= p/q the
+// rounded quotient cannot exceed RN(p/q); if it is larger, it is larger by at least 1/(union*q) > 2^-41, hundreds of
+// ulps above t_d, for union < 2^31 and q <= 1000.)  Two 64-bit products and one compare instead of the 12-instruction
+// screening test: the candidate x kept tests are what the training configuration (12000 -> 2000) spends its time on.
+// returns 1 = suppressed, 0 = survives, 2 = uncertain (union <= 0: degenerate boxes go to the exact predicate)
+__device__ __forceinline__ int screen_rational(int ax1, int ay1, int ax2, int ay2, int a_area, int bx1, int by1,
+                                               int bx2, int by2, int b_area, int p, int q) {
+  const int iw = min(ax2, bx2) - max(ax1, bx1) + 1;
+  const int ih = min(ay2, by2) - max(ay1, by1) + 1;
+  const int inter = max(iw, 0) * max(ih, 0);
+  const int uni = a_area + b_area - inter;
+  const bool over = (long long)inter * q > (long long)uni * p;
+  return uni > 0 ? (over ? 1 : 0) : 2;
+}
+
 // Thread-block clusters: an image may be given a cluster of CL CTAs (1, 2, 4 or 8 SMs).  Every CTA
 // holds the full candidate array, the kept list is dealt round-robin over the CTAs (kept j lives in CTA
 // j % CL), each CTA tests the tile's 64 candidates against ITS share, the 64-bit partial masks are
@@ -83,7 +101,8 @@ __device__ __forceinline__ int screen_i16(int ax1, int ay1, int ax2, int ay2, in
 __global__ void __launch_bounds__(NMS_THREADS, 1)
 nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ scores_all,
                const int* __restrict__ n_all, int n_max, double thresh, int max_boxes, int max_keep,
-               int keep_local, int buf_elems, int cl, int* __restrict__ order_all, int* __restrict__ keep_index,
+               int keep_local, int buf_elems, int cl, int rat_p, int rat_q, int* __restrict__ order_all,
+               int* __restrict__ keep_index,
                int* __restrict__ keep_count, BoxI16* __restrict__ keep_boxes,
                float* __restrict__ keep_scores) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -186,10 +205,18 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
     bool sup = false;
     if (fast_ok) {
       int flags = 0;                               // bit0: suppressed by some kept box, bit1: some test uncertain
+      if (rat_q > 0) {
 #pragma unroll 4
-      for (int j = slice; j < nlocal; j += SLICES) {
-        const int4 kb = kept_box[j];
-        flags |= screen_i16(kb.x, kb.y, kb.z, kb.w, kept_area[j], bx1, by1, bx2, by2, b_area, t_fix);
+        for (int j = slice; j < nlocal; j += SLICES) {
+          const int4 kb = kept_box[j];
+          flags |= screen_rational(kb.x, kb.y, kb.z, kb.w, kept_area[j], bx1, by1, bx2, by2, b_area, rat_p, rat_q);
+        }
+      } else {
+#pragma unroll 4
+        for (int j = slice; j < nlocal; j += SLICES) {
+          const int4 kb = kept_box[j];
+          flags |= screen_i16(kb.x, kb.y, kb.z, kb.w, kept_area[j], bx1, by1, bx2, by2, b_area, t_fix);
+        }
       }
       sup = (flags & 1) != 0;
       if (!sup && (flags & 2)) {                   // rare: redo this candidate's share with the exact predicate
@@ -360,8 +387,16 @@ int launch_nms_i16(frcnn_handle* h, cudaStream_t stream, const int16_t* boxes, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // threshold as an exact ratio of small integers (0.7 -> 7/10), if it is one: see screen_rational
+  int rat_p = 0, rat_q = 0;
+  if (thresh > 1e-6 && thresh < 1.0) {
+    for (int q = 2; q <= 1000 && rat_q == 0; ++q) {
+      const double p = nearbyint(thresh * q);
+      if (p >= 1.0 && p < (double)q && p / (double)q == thresh) { rat_p = (int)p; rat_q = q; }
+    }
+  }
   FRCNN_CUDA(h, cudaLaunchKernelEx(&cfg, nms_i16_kernel, reinterpret_cast<const BoxI16*>(boxes), scores, n, n_max, thresh,
-                                   max_boxes, max_keep, keep_local, buf_elems, cl, reinterpret_cast<int*>(ws), keep_index,
+                                   max_boxes, max_keep, keep_local, buf_elems, cl, rat_p, rat_q, reinterpret_cast<int*>(ws), keep_index,
                                    keep_count, reinterpret_cast<BoxI16*>(keep_boxes), keep_scores));
   FRCNN_LAUNCH_CHECK(h, "nms_i16_kernel");
   return FRCNN_OK;
