@@ -246,7 +246,14 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
           if (j > i && j < tile_n) {
             const BoxI16 c = sorted[base + j];
             const int c_area = (c.x2 - c.x1 + 1) * (c.y2 - c.y1 + 1);
-            if (suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives)) {
+            bool hit;
+            if (rat_q > 0) {
+              const int r = screen_rational(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, rat_p, rat_q);
+              hit = r == 1 || (r == 2 && suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives));
+            } else {
+              hit = suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives);
+            }
+            if (hit) {
               if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
             }
           }
