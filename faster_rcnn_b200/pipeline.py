@@ -248,20 +248,42 @@ class DetTrainingPipeline:
         n_gt = np.array([len(g) for g, _ in per], np.int32)
         return self.ctx.to_device(gt), self.ctx.to_device(gt_cls), self.ctx.to_device(n_gt)
 
-    def targets(self, cls, regr, gt, gt_cls, n_gt):
+    def targets(self, cls, regr, gt, gt_cls, n_gt, chunk=32):
         """CUDA tensors in -> (rois (B,S,4) i16, y_class_num (B,S,K) i32, y_transform (B,S,8(K-1)) f32) on the device and
-        has_rois (B,) bool on the host."""
+        has_rois (B,) bool on the host.  The batch is enqueued in chunks of `chunk` images; the host draws the
+        mini-batches of chunk i (in image order, so the RNG stream is the per-image one) while the GPU is still
+        labelling chunks i+1.."""
         from .det_util import _get_det_samples
-        rois, _, count = ops.proposals(regr, cls, self.anchor_dims, self.stride, self.k, self.thresh, self.max_boxes)
-        l_rois, y_cls, y_tr, _, m = ops.label_rois(rois, gt, gt_cls, n_gt, len(self.class_mapping), n_roi=count)
-        found = self.ctx.to_host((y_cls[:, :, -1] == 0).to(torch.uint8))          # positives = not background
-        m_host = self.ctx.to_host(m)
-        index = np.full((len(m_host), self.num_rois), -1, np.int32)
-        for b, mb in enumerate(m_host.tolist()):                                   # RNG draws in image order
-            if mb > 0:
-                index[b] = _get_det_samples(found[b, :mb] == 1, self.num_rois)
-        out = ops.gather_det_samples(l_rois, y_cls, y_tr, self.ctx.to_device(index))
-        return out + (m_host > 0,)
+        b, dev = cls.shape[0], self.ctx.device
+        stream = torch.cuda.current_stream(dev)
+        staged = []
+        for lo in range(0, b, chunk):
+            hi = min(b, lo + chunk)
+            rois, _, count = ops.proposals(regr[lo:hi], cls[lo:hi], self.anchor_dims, self.stride, self.k, self.thresh,
+                                           self.max_boxes)
+            l_rois, y_cls, y_tr, _, m = ops.label_rois(rois, gt[lo:hi], gt_cls[lo:hi], n_gt[lo:hi],
+                                                       len(self.class_mapping), n_roi=count)
+            found_d = (y_cls[:, :, -1] == 0).to(torch.uint8)                      # positives = not background
+            found_h = torch.empty(found_d.shape, dtype=torch.uint8).pin_memory()
+            m_h = torch.empty(m.shape, dtype=m.dtype).pin_memory()
+            found_h.copy_(found_d, non_blocking=True)
+            m_h.copy_(m, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            staged.append((l_rois, y_cls, y_tr, found_h, m_h, ev))
+        outs, has = [], []
+        for l_rois, y_cls, y_tr, found_h, m_h, ev in staged:
+            ev.synchronize()
+            found, m_host = found_h.numpy(), m_h.numpy()
+            index = np.full((len(m_host), self.num_rois), -1, np.int32)
+            for i, mb in enumerate(m_host.tolist()):                               # RNG draws in image order
+                if mb > 0:
+                    index[i] = _get_det_samples(found[i, :mb] == 1, self.num_rois)
+            index_h = torch.from_numpy(index).pin_memory()
+            outs.append(ops.gather_det_samples(l_rois, y_cls, y_tr, index_h.to(dev, non_blocking=True)))
+            has.append(m_host > 0)
+        rois, y_cls, y_tr = (torch.cat([o[j] for o in outs]) for j in range(3))
+        return rois, y_cls, y_tr, np.concatenate(has)
 
     def __call__(self, cls, regr, feat, images):
         """Host or device arrays + the images' ground truth -> (rois, y_class_num, y_transform, pooled, has_rois):
