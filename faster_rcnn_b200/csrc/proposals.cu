@@ -115,26 +115,34 @@ __device__ __forceinline__ int block_inclusive_scan(int v, int* warp_tot) {
 template <int E>
 __device__ __forceinline__ int pad_slot(int e) { return e + e / E; }
 
-// Block-wide exact selection: returns a splitter T such that exactly `rank` keys are >= T (keys are
-// unique and non-zero; the caller guarantees 0 < rank < number of valid keys).  MSB-first radix
-// select, 11-bit digits, one shared histogram fed by warp-aggregated atomics (__match_any_sync: one
-// atomic per distinct digit per warp), suffix scan over the bins.  The pass at which the splitter's
-// bucket holds exactly the keys still needed ends it (3 passes for tie-free float scores).
+// Block-wide exact selection of up to TWO ranks in one set of sweeps: splitter T_s such that exactly `rank_s` keys are
+// >= T_s (keys are unique and non-zero; the caller guarantees 0 < rank < number of valid keys).  MSB-first radix
+// select, 11-bit digits, shared histograms fed by warp-aggregated atomics (__match_any_sync: one atomic per distinct
+// digit per warp), suffix scan over the bins.  The pass at which a splitter's bucket holds exactly the keys still
+// needed ends that select (3 passes for tie-free float scores).  A CTA in the middle of the rank range needs both of
+// its slice bounds; selecting them jointly reads the keys once per pass instead of twice, and while the two prefixes
+// still agree (always in the first pass) one histogram serves both.
 // Keys are fetched 8 per thread before any is consumed, which hides the L2 latency.
 constexpr int TOPK_U = 8;
-__device__ unsigned long long radix_select(const unsigned long long* __restrict__ keys, int n, int rank,
-                                           unsigned* hist, int* warp_tot, unsigned long long* s_prefix,
-                                           int* s_need, int* s_done) {
+__device__ void radix_select2(const unsigned long long* __restrict__ keys, int n, int rank_a, int rank_b, bool use_b,
+                              unsigned* hist /* [2][TOPK_BINS] */, int* warp_tot, unsigned long long* s_prefix /* [2] */,
+                              int* s_need /* [2] */, int* s_done /* [2] */, unsigned long long& t_a,
+                              unsigned long long& t_b) {
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) { *s_prefix = 0ull; *s_need = rank; *s_done = 0; }
+  if (tid == 0) {
+    s_prefix[0] = s_prefix[1] = 0ull;
+    s_need[0] = rank_a; s_need[1] = rank_b;
+    s_done[0] = 0; s_done[1] = use_b ? 0 : 1;
+  }
   __syncthreads();
   for (int hi = 64; hi > 0;) {
     const int bits = hi < TOPK_BITS ? hi : TOPK_BITS;
     const int shift = hi - bits;
-    for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = 0u;
+    for (int i = tid; i < 2 * TOPK_BINS; i += TOPK_THREADS) hist[i] = 0u;
     __syncthreads();
-    const unsigned long long prefix = *s_prefix;
-    const int need = *s_need;
+    const unsigned long long pa = s_prefix[0], pb = s_prefix[1];
+    const bool da = s_done[0] != 0, db = s_done[1] != 0;
+    const bool same = !da && !db && (hi == 64 || (pa >> hi) == (pb >> hi));   // identical histograms: build A's only
     for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
       unsigned long long kk[TOPK_U];
 #pragma unroll
@@ -145,37 +153,45 @@ __device__ unsigned long long radix_select(const unsigned long long* __restrict_
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
         const unsigned long long key = kk[u];
-        const bool in = key != 0ull && (hi == 64 || (key >> hi) == (prefix >> hi));
-        const unsigned digit = in ? (unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u)) : 0xffffffffu;
+        const bool in_a = !da && key != 0ull && (hi == 64 || (key >> hi) == (pa >> hi));
+        const unsigned digit = (unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u));
         if (hi == 64) {
           // first pass: a handful of distinct digits per warp (sign + exponent bits) -> aggregate
-          const unsigned peers = __match_any_sync(0xffffffffu, digit);
-          if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
-        } else if (in) {
-          atomicAdd(&hist[digit], 1u);              // later passes: few keys left and their digits are spread out
+          const unsigned peers = __match_any_sync(0xffffffffu, in_a ? digit : 0xffffffffu);
+          if (in_a && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+        } else {
+          if (in_a) atomicAdd(&hist[digit], 1u);     // later passes: few keys left and their digits are spread out
+          if (!db && !same && key != 0ull && (key >> hi) == (pb >> hi)) atomicAdd(&hist[TOPK_BINS + digit], 1u);
         }
       }
     }
     __syncthreads();
-    // suffix scan from the top bin: thread t owns bins BINS-1-2t (c0) and BINS-2-2t (c1)
-    const int c0 = (int)hist[TOPK_BINS - 1 - 2 * tid], c1 = (int)hist[TOPK_BINS - 2 - 2 * tid];
-    const int incl = block_inclusive_scan(c0 + c1, warp_tot);
-    const int excl = incl - c0 - c1;
-    int d = -1, rest = 0, cnt = 0;
-    if (excl < need && excl + c0 >= need) { d = TOPK_BINS - 1 - 2 * tid; rest = need - excl; cnt = c0; }
-    else if (excl + c0 < need && incl >= need) { d = TOPK_BINS - 2 - 2 * tid; rest = need - excl - c0; cnt = c1; }
-    if (d >= 0) {                                   // exactly one thread
-      *s_prefix = prefix | ((unsigned long long)d << shift);
-      *s_need = rest;
-      if (shift == 0 || cnt == rest) *s_done = 1;   // bucket taken whole: the low bits are free
+#pragma unroll
+    for (int sel = 0; sel < 2; ++sel) {
+      if (sel == 0 ? da : db) continue;              // block-uniform
+      const unsigned* hh = hist + ((sel == 1 && !same) ? TOPK_BINS : 0);
+      const unsigned long long prefix = sel == 0 ? pa : pb;
+      const int need = s_need[sel];
+      // suffix scan from the top bin: thread t owns bins BINS-1-2t (c0) and BINS-2-2t (c1)
+      const int c0 = (int)hh[TOPK_BINS - 1 - 2 * tid], c1 = (int)hh[TOPK_BINS - 2 - 2 * tid];
+      const int incl = block_inclusive_scan(c0 + c1, warp_tot);
+      const int excl = incl - c0 - c1;
+      int d = -1, rest = 0, cnt = 0;
+      if (excl < need && excl + c0 >= need) { d = TOPK_BINS - 1 - 2 * tid; rest = need - excl; cnt = c0; }
+      else if (excl + c0 < need && incl >= need) { d = TOPK_BINS - 2 - 2 * tid; rest = need - excl - c0; cnt = c1; }
+      if (d >= 0) {                                  // exactly one thread
+        s_prefix[sel] = prefix | ((unsigned long long)d << shift);
+        s_need[sel] = rest;
+        if (shift == 0 || cnt == rest) s_done[sel] = 1;   // bucket taken whole: the low bits are free
+      }
     }
     __syncthreads();
     hi = shift;
-    if (*s_done) break;
+    if (s_done[0] && s_done[1]) break;
   }
-  const unsigned long long t = *s_prefix;
+  t_a = s_prefix[0];
+  t_b = s_prefix[1];
   __syncthreads();
-  return t;
 }
 
 // `splits` CTAs per image.  CTA r produces ranks [r*k/splits, (r+1)*k/splits) of the descending top-k
@@ -192,10 +208,10 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
             int* __restrict__ out_count) {
   constexpr int M = TOPK_THREADS * E;                 // sort size (power of two), >= slice length
   extern __shared__ __align__(16) unsigned long long sbuf[];      // pad_slot<E>(M) entries
-  __shared__ unsigned hist[TOPK_BINS];
+  __shared__ unsigned hist[2 * TOPK_BINS];
   __shared__ int warp_tot[TOPK_WARPS];
-  __shared__ unsigned long long s_prefix;
-  __shared__ int s_need, s_count, s_done;
+  __shared__ unsigned long long s_prefix[2];
+  __shared__ int s_need[2], s_done[2], s_count;
 
   const int img = blockIdx.x / splits, part = blockIdx.x - img * splits;
   const unsigned long long* keys = keys_all + (size_t)img * n;
@@ -212,8 +228,19 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
   // splitters: keys >= t_lo and < t_hi are exactly the ranks [first, last)
   unsigned long long t_hi = ~0ull, t_lo = 1ull;
   if (first < last) {
-    if (first > 0) t_hi = radix_select(keys, n, first, hist, warp_tot, &s_prefix, &s_need, &s_done);
-    if (last < n_valid) t_lo = radix_select(keys, n, last, hist, warp_tot, &s_prefix, &s_need, &s_done);
+    const bool need_hi = first > 0, need_lo = last < n_valid;
+    unsigned long long ta = 0ull, tb = 0ull;
+    if (need_hi && need_lo) {
+      radix_select2(keys, n, first, last, true, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
+      t_hi = ta;
+      t_lo = tb;
+    } else if (need_hi) {
+      radix_select2(keys, n, first, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
+      t_hi = ta;
+    } else if (need_lo) {
+      radix_select2(keys, n, last, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
+      t_lo = ta;
+    }
   }
 
   // compaction of the slice into shared memory (order irrelevant, sorted next)
