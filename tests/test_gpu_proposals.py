@@ -340,3 +340,21 @@ def test_pipeline_cuda_graph_replay_equals_eager(ops):
         torch.cuda.synchronize()
         for w, g in zip(want, got):
             assert torch.equal(w, g)
+
+
+@pytest.mark.parametrize("levels,k,max_boxes", [(20, 8000, 300), (3, 3000, 300), (1, 500, 64)])
+def test_fused_proposals_with_tied_scores(ops, levels, k, max_boxes):
+    """Saturated / quantised RPN scores (a trained sigmoid head outputs exact 1.0s): the top-k boundary and the NMS visit
+    order among equal scores follow the documented total order (two stable sorts, like the reference's argsort calls
+    with kind='stable'), also on the fused decode -> top-k -> NMS path."""
+    dims, cls, regr = _synth(38, 63, [128, 256, 512], 31, True)
+    cls = (np.ceil(cls * levels) / levels).astype(np.float32)
+    dense = host(ops.decode_topk(dev(regr), dev(cls), dims, 16, k, want_dense=True)[4])[0]
+    wb, wp, widx = O.topk_proposals(dense.copy(), cls.reshape(-1), k, stable=True)
+    boxes, scores, index, count = ops.decode_topk(dev(regr), dev(cls), dims, 16, k)
+    n = int(host(count)[0])
+    assert n == len(wb) and np.array_equal(host(index)[0, :n], widx) and np.array_equal(host(boxes)[0, :n], wb)
+    pick = O.greedy_nms(wb, wp, 0.7, max_boxes, stable=True)
+    rois, sc, cnt = ops.proposals(dev(regr), dev(cls), dims, 16, k, 0.7, max_boxes)
+    m = int(host(cnt)[0])
+    assert m == len(pick) and np.array_equal(host(rois)[0, :m], wb[pick]) and np.array_equal(host(sc)[0, :m], wp[pick])
