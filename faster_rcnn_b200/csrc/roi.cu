@@ -174,31 +174,39 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
     return;
   }
   const size_t row_stride = (size_t)W * C;
+  const size_t row_bytes = row_stride * 4;
   if (MODE == FRCNN_ROI_RESIZE) {
-    // x taps as float offsets from the row pointer, once per thread: the per-output address arithmetic was 38 of the
-    // 80 SASS instructions of this loop (64-bit multiplies per tap), and this kernel runs into the 1000 W power cap
-    // in sustained operation (bench.py --steps 300: sw_power_cap, 0.96 -> 1.05 ms), so instructions are energy.
-    for (int ph = ph0; ph < ph1; ++ph) {
-      const int4 ty = s_tap[ph];
-      const char* row_lo = reinterpret_cast<const char*>(f + (size_t)(ty.x & 0xffff) * row_stride);
-      const char* row_hi = reinterpret_cast<const char*>(f + (size_t)(ty.x >> 16) * row_stride);
-      const float ly = __int_as_float(ty.y);
-      float* o = out + obase + (size_t)ph * P * C;
-      // Measured and rejected (profiles/README.md): L1-bypassing tap loads (ld.global.nc.L1::no_allocate and
-      // ld.global.cg: 1.10-1.12 ms vs 0.92 ms -- the 34 % L1 hit rate matters), issuing the tap loads of 2/4/7 outputs ahead
-      // (no gain: the kernel is bound by L1/TEX + DRAM-write throughput, not load latency) and keeping
-      // the last two source columns in registers (fewer loads, but the extra registers cost more
-      // occupancy than the loads saved).
-      for (int pw = 0; pw < P; ++pw, o += C) {
-        const int4 tx = s_xoff[pw];                 // (byte offset of xlo, of xhi, bits(lx), -), unsigned 32-bit
-        const float lx = __int_as_float(tx.z);
-        const unsigned bl_off = (unsigned)tx.x, bh_off = (unsigned)tx.y;
-        const float4 tl = ldg_f4(reinterpret_cast<const float*>(row_lo + bl_off));
-        const float4 tr = ldg_f4(reinterpret_cast<const float*>(row_lo + bh_off));
-        const float4 bl = ldg_f4(reinterpret_cast<const float*>(row_hi + bl_off));
-        const float4 br = ldg_f4(reinterpret_cast<const float*>(row_hi + bh_off));
-        const float4 top = lerp4(tl, tr, lx), bot = lerp4(bl, br, lx);
-        st_cs_f4(o, lerp4(top, bot, ly));
+    // Loop order pw (outer) / ph (inner): the x taps of a column stay in registers (byte offsets from the row pointer;
+    // the per-output address arithmetic was 38 of the 80 SASS instructions of the first version, and this kernel
+    // runs into the 1000 W power cap in sustained operation, so instructions are energy), and when the source row of
+    // this output's top taps is the row of the previous output's bottom taps (crops lower than 2P rows) the already
+    // interpolated bottom value is carried over instead of being loaded and interpolated again -- identical
+    // arithmetic on identical inputs, so the result is bit for bit the same.
+    const char* fb = reinterpret_cast<const char*>(f);
+    for (int pw = 0; pw < P; ++pw) {
+      const int4 tx = s_xoff[pw];                   // (byte offset of xlo, of xhi, bits(lx), -), unsigned 32-bit
+      const float lx = __int_as_float(tx.z);
+      const unsigned bl_off = (unsigned)tx.x, bh_off = (unsigned)tx.y;
+      float* o = out + obase + ((size_t)ph0 * P + pw) * C;
+      float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+      int carry_row = -1;
+      for (int ph = ph0; ph < ph1; ++ph, o += (size_t)P * C) {
+        const int4 ty = s_tap[ph];
+        const int ylo = ty.x & 0xffff, yhi = ty.x >> 16;
+        const char* row_hi = fb + (size_t)yhi * row_bytes;
+        float4 top;
+        if (ylo == carry_row) {                     // warp-uniform
+          top = carry;
+        } else {
+          const char* row_lo = fb + (size_t)ylo * row_bytes;
+          top = lerp4(ldg_f4(reinterpret_cast<const float*>(row_lo + bl_off)),
+                      ldg_f4(reinterpret_cast<const float*>(row_lo + bh_off)), lx);
+        }
+        const float4 bot = lerp4(ldg_f4(reinterpret_cast<const float*>(row_hi + bl_off)),
+                                 ldg_f4(reinterpret_cast<const float*>(row_hi + bh_off)), lx);
+        st_cs_f4(o, lerp4(top, bot, __int_as_float(ty.y)));
+        carry = bot;
+        carry_row = yhi;
       }
     }
   } else {
