@@ -183,30 +183,61 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
     // interpolated bottom value is carried over instead of being loaded and interpolated again -- identical
     // arithmetic on identical inputs, so the result is bit for bit the same.
     const char* fb = reinterpret_cast<const char*>(f);
-    for (int pw = 0; pw < P; ++pw) {
-      const int4 tx = s_xoff[pw];                   // (byte offset of xlo, of xhi, bits(lx), -), unsigned 32-bit
-      const float lx = __int_as_float(tx.z);
-      const unsigned bl_off = (unsigned)tx.x, bh_off = (unsigned)tx.y;
-      float* o = out + obase + ((size_t)ph0 * P + pw) * C;
-      float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
-      int carry_row = -1;
-      for (int ph = ph0; ph < ph1; ++ph, o += (size_t)P * C) {
-        const int4 ty = s_tap[ph];
-        const int ylo = ty.x & 0xffff, yhi = ty.x >> 16;
-        const char* row_hi = fb + (size_t)yhi * row_bytes;
-        float4 top;
-        if (ylo == carry_row) {                     // warp-uniform
-          top = carry;
-        } else {
-          const char* row_lo = fb + (size_t)ylo * row_bytes;
-          top = lerp4(ldg_f4(reinterpret_cast<const float*>(row_lo + bl_off)),
-                      ldg_f4(reinterpret_cast<const float*>(row_lo + bh_off)), lx);
+    if (s_crop.w <= s_crop.z) {                     // crop height <= width: more row reuse than column reuse
+      for (int pw = 0; pw < P; ++pw) {
+        const int4 tx = s_xoff[pw];                 // (byte offset of xlo, of xhi, bits(lx), -), unsigned 32-bit
+        const float lx = __int_as_float(tx.z);
+        const unsigned bl_off = (unsigned)tx.x, bh_off = (unsigned)tx.y;
+        float* o = out + obase + ((size_t)ph0 * P + pw) * C;
+        float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+        int carry_row = -1;
+        for (int ph = ph0; ph < ph1; ++ph, o += (size_t)P * C) {
+          const int4 ty = s_tap[ph];
+          const int ylo = ty.x & 0xffff, yhi = ty.x >> 16;
+          const char* row_hi = fb + (size_t)yhi * row_bytes;
+          float4 top;
+          if (ylo == carry_row) {                   // warp-uniform
+            top = carry;
+          } else {
+            const char* row_lo = fb + (size_t)ylo * row_bytes;
+            top = lerp4(ldg_f4(reinterpret_cast<const float*>(row_lo + bl_off)),
+                        ldg_f4(reinterpret_cast<const float*>(row_lo + bh_off)), lx);
+          }
+          const float4 bot = lerp4(ldg_f4(reinterpret_cast<const float*>(row_hi + bl_off)),
+                                   ldg_f4(reinterpret_cast<const float*>(row_hi + bh_off)), lx);
+          st_cs_f4(o, lerp4(top, bot, __int_as_float(ty.y)));
+          carry = bot;
+          carry_row = yhi;
         }
-        const float4 bot = lerp4(ldg_f4(reinterpret_cast<const float*>(row_hi + bl_off)),
-                                 ldg_f4(reinterpret_cast<const float*>(row_hi + bh_off)), lx);
-        st_cs_f4(o, lerp4(top, bot, __int_as_float(ty.y)));
-        carry = bot;
-        carry_row = yhi;
+      }
+    } else {                                        // taller than wide: ph outer, the right taps become the next left taps
+      for (int ph = ph0; ph < ph1; ++ph) {
+        const int4 ty = s_tap[ph];
+        const char* row_lo = fb + (size_t)(ty.x & 0xffff) * row_bytes;
+        const char* row_hi = fb + (size_t)(ty.x >> 16) * row_bytes;
+        const float ly = __int_as_float(ty.y);
+        float* o = out + obase + (size_t)ph * P * C;
+        float4 ctop = make_float4(0.f, 0.f, 0.f, 0.f), cbot = ctop;
+        unsigned carry_off = 0xffffffffu;
+        for (int pw = 0; pw < P; ++pw, o += C) {
+          const int4 tx = s_xoff[pw];
+          const float lx = __int_as_float(tx.z);
+          const unsigned bl_off = (unsigned)tx.x, bh_off = (unsigned)tx.y;
+          float4 tl, bl;
+          if (bl_off == carry_off) {                // warp-uniform
+            tl = ctop;
+            bl = cbot;
+          } else {
+            tl = ldg_f4(reinterpret_cast<const float*>(row_lo + bl_off));
+            bl = ldg_f4(reinterpret_cast<const float*>(row_hi + bl_off));
+          }
+          const float4 tr = ldg_f4(reinterpret_cast<const float*>(row_lo + bh_off));
+          const float4 br = ldg_f4(reinterpret_cast<const float*>(row_hi + bh_off));
+          st_cs_f4(o, lerp4(lerp4(tl, tr, lx), lerp4(bl, br, lx), ly));
+          ctop = tr;
+          cbot = br;
+          carry_off = bh_off;
+        }
       }
     }
   } else {
