@@ -159,7 +159,7 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
   }
   __syncthreads();
   // blockIdx.y = channel block * ph_groups + group: small max-mode launches (2000 RoIs of ONE image are 2.7 waves of
-  // CTAs) are cut into P row groups per RoI so that the last wave is nearly full; everything else uses one group.
+  // CTAs) are cut into two row groups per RoI so that the last wave is fuller; everything else uses one group.
   const int cblock = blockIdx.y / ph_groups, grp = blockIdx.y - cblock * ph_groups;
   const int ph0 = grp * P / ph_groups, ph1 = (grp + 1) * P / ph_groups;
   const int c = (cblock * ROI_FWD_THREADS + threadIdx.x) * 4;
@@ -241,31 +241,59 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
       }
     }
   } else {
-    for (int ph = ph0; ph < ph1; ++ph) {
-      const int ya = s_tap[ph].x & 0xffff, yb = s_tap[ph].x >> 16;
-      for (int pw = 0; pw < P; ++pw) {
-        const int xa = s_tap[pw].z & 0xffff, xb = s_tap[pw].z >> 16;
-        // running pointers instead of per-cell 64-bit index arithmetic (8 of the 22 SASS instructions per cell)
-        const float* rp = f + ((size_t)ya * W + xa) * C;
-        int cell_row = ya * W + xa;
-        float4 best = ldg_f4(rp);
-        int4 arg = make_int4(cell_row, cell_row, cell_row, cell_row);
-        for (int y = ya; y < yb; ++y, rp += row_stride, cell_row += W) {
-          const float* cp = rp;
-          int cell = cell_row;
-#pragma unroll 4
-          for (int x = xa; x < xb; ++x, cp += C, ++cell) {
-            const float4 v = ldg_f4(cp);
-            if (v.x > best.x) { best.x = v.x; arg.x = cell; }
-            if (v.y > best.y) { best.y = v.y; arg.y = cell; }
-            if (v.z > best.z) { best.z = v.z; arg.z = cell; }
-            if (v.w > best.w) { best.w = v.w; arg.w = cell; }
+    // MAX mode, pw outer / ph inner.  Consecutive bins of a column share their boundary row whenever (ph+1)*h is
+    // not a multiple of P; that row is scanned ONCE into a row tracker, merged into the upper bin (strict '>' keeps
+    // the earlier rows on ties = first maximum in row-major order) and becomes the initial value of the lower bin.
+    // The kernel is issue bound (ncu: 77 %) on the 12 compare/select instructions per cell, so every cell that is not
+    // visited twice counts (21 row scans per column become 15 + 6 merges at h = 15).
+#define FRCNN_SCAN_ROW(Y, B, A, INIT)                                                         \
+  {                                                                                            \
+    const float* cp_ = f + ((size_t)(Y) * W + xa) * C;                                         \
+    int cell_ = (Y) * W + xa;                                                                  \
+    int x_ = xa;                                                                               \
+    if (INIT) { B = ldg_f4(cp_); A = make_int4(cell_, cell_, cell_, cell_); ++x_; cp_ += C; ++cell_; } \
+    _Pragma("unroll 4") for (; x_ < xb; ++x_, cp_ += C, ++cell_) {                             \
+      const float4 v_ = ldg_f4(cp_);                                                           \
+      if (v_.x > B.x) { B.x = v_.x; A.x = cell_; }                                             \
+      if (v_.y > B.y) { B.y = v_.y; A.y = cell_; }                                             \
+      if (v_.z > B.z) { B.z = v_.z; A.z = cell_; }                                             \
+      if (v_.w > B.w) { B.w = v_.w; A.w = cell_; }                                             \
+    }                                                                                          \
+  }
+    for (int pw = 0; pw < P; ++pw) {
+      const int xa = s_tap[pw].z & 0xffff, xb = s_tap[pw].z >> 16;
+      float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+      int4 ra = make_int4(0, 0, 0, 0);
+      int row_y = -1;                               // source row held by the row tracker (rb, ra)
+      for (int ph = ph0; ph < ph1; ++ph) {
+        const int ya = s_tap[ph].x & 0xffff, yb = s_tap[ph].x >> 16;
+        const int last = yb - 1;
+        const bool shared_next = ph + 1 < ph1 && (s_tap[ph + 1].x & 0xffff) == last;
+        float4 best = rb;
+        int4 arg = ra;
+        bool started = row_y == ya;                 // this bin starts on the row the previous bin ended on
+        const int y_end = shared_next ? last : yb;  // rows scanned straight into the bin tracker: [y0, y_end)
+        for (int y = started ? ya + 1 : ya; y < y_end; ++y) {
+          if (started) FRCNN_SCAN_ROW(y, best, arg, false) else FRCNN_SCAN_ROW(y, best, arg, true)
+          started = true;
+        }
+        if (shared_next) {
+          if (row_y != last) { FRCNN_SCAN_ROW(last, rb, ra, true) row_y = last; }
+          if (!started) {
+            best = rb;
+            arg = ra;
+          } else {                                  // merging a row that is already in `best` is a no-op (strict '>')
+            if (rb.x > best.x) { best.x = rb.x; arg.x = ra.x; }
+            if (rb.y > best.y) { best.y = rb.y; arg.y = ra.y; }
+            if (rb.z > best.z) { best.z = rb.z; arg.z = ra.z; }
+            if (rb.w > best.w) { best.w = rb.w; arg.w = ra.w; }
           }
         }
         st_cs_f4(out + obase + (size_t)(ph * P + pw) * C, best);
         st_cs_i4(argmax + obase + (size_t)(ph * P + pw) * C, arg);
       }
     }
+#undef FRCNN_SCAN_ROW
   }
 }
 
@@ -688,10 +716,11 @@ int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
       (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
       (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0)) {
     const int cblocks = (C / 4 + ROI_FWD_THREADS - 1) / ROI_FWD_THREADS;
-    // max mode, fewer than 8 waves of CTAs (20 resident per SM): split every RoI into P row groups (same-box A/B at
-    // 2000 RoIs x 1 image: 0.262 -> 0.232 ms; resize mode got slower with the split, 0.109 -> 0.117 ms, and keeps one)
+    // max mode, fewer than 8 waves of CTAs (20 resident per SM): split every RoI into two row groups (same-box A/B at
+    // 2000 RoIs x 1 image: 0.252 ms with one group, 0.236 with two or three, 0.265 with P groups -- more groups break
+    // the boundary-row carry-over; resize mode got slower with any split and keeps one)
     const long long ctas = (long long)N * cblocks * batch;
-    const int ph_groups = (mode == FRCNN_ROI_MAX && ctas < 8LL * 20 * h->sm_count && (long long)cblocks * P <= 65535) ? P : 1;
+    const int ph_groups = (mode == FRCNN_ROI_MAX && P >= 2 && ctas < 8LL * 20 * h->sm_count) ? 2 : 1;
     dim3 grid(N, cblocks * ph_groups, batch);
     if (mode == FRCNN_ROI_RESIZE)
       roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, ph_groups, out, argmax);
