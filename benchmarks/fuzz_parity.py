@@ -4,8 +4,9 @@
     python benchmarks/fuzz_parity.py [--cases 300] [--seed 0]
 
 Draws shapes / thresholds / limits the fixed test parametrisations do not cover (NMS stopping inside a tile, 1-box
-inputs, heavy ties, thresholds at 0 and 1, odd channel counts and pool sizes, ragged batches) and compares every
-result bit for bit with the oracle (resize-mode RoI backward: 1e-5 relative).  Prints one JSON summary line."""
+inputs, heavy ties, thresholds at 0 and 1, odd channel counts and pool sizes, ragged batches, RoI labelling, detector
+post-processing) and compares every result bit for bit with the oracle (resize-mode RoI backward: 1e-5 relative;
+log()-based regression targets: 1 float32 ulp).  Prints one JSON summary line."""
 import argparse
 import json
 import os
@@ -104,13 +105,49 @@ def case_labels(rng):
     return bool(ok), dict(kind="labels", rows=rows, cols=cols, g=g)
 
 
+def _ulp_close(got, want, max_ulp=1):
+    gi, wi = np.ascontiguousarray(got, np.float32).view(np.int32).astype(np.int64), np.ascontiguousarray(want, np.float32).view(np.int32).astype(np.int64)
+    gi = np.where(gi < 0, -(gi & 0x7fffffff), gi)
+    wi = np.where(wi < 0, -(wi & 0x7fffffff), wi)
+    return got.shape == want.shape and (got.size == 0 or int(np.abs(gi - wi).max()) <= max_ulp)
+
+
+def case_label_rois(rng):
+    rows, cols = int(rng.integers(4, 40)), int(rng.integers(4, 64))
+    n, g = int(rng.choice([1, 17, 300, 2000])), int(rng.choice([1, 3, 12, 50]))
+    rois = synth.random_rois(n, rows, cols, int(rng.integers(1 << 30)))
+    gts = synth.gt_boxes(g, cols * 16, rows * 16, int(rng.integers(1 << 30)))
+    gt64 = np.array([[v * (1 / 16) for v in x[1:]] for x in gts], np.float64)
+    gidx = np.array([synth.VOC_CLASS_MAPPING[x[0]] for x in gts], np.int32)
+    out = ops.label_rois(dev(rois[None]), dev(gt64[None]), dev(gidx[None]), dev(np.array([g], np.int32)), 21)
+    e_rois, w_cls, w_tr = O.label_rois(rois, gt64, gidx, 21)
+    m = int(host(out[4])[0])
+    ok = m == len(e_rois) and np.array_equal(host(out[0])[0, :m], e_rois) and np.array_equal(host(out[1])[0, :m], w_cls)
+    ok = ok and _ulp_close(host(out[2])[0, :m], w_tr)           # log() in the targets: <= 1 ulp after the f32 store
+    return bool(ok), dict(kind="label_rois", n=n, g=g)
+
+
+def case_postprocess(rng):
+    m, k = int(rng.choice([64, 128, 320])), 21
+    rois = synth.random_rois(m, 37, 62, int(rng.integers(1 << 30)))
+    oc, orr = synth.detector_outputs(m, k, int(rng.integers(1 << 30)))
+    ratio, thr = float(rng.choice([0.75, 1.0, 1.6, 2.2])), float(rng.choice([0.0, 0.2, 0.5]))
+    boxes, probs, dcls, count = ops.det_postprocess(dev(rois[None]), dev(oc[None]), dev(orr[None]), dev(np.array([ratio])), 20, 16, thr)
+    want = O.det_postprocess(rois, oc, orr, 20, 16, ratio, det_threshold=thr)
+    c = int(host(count)[0])
+    ok = c == len(want)
+    for i, (wc, wbox, wp) in enumerate(want if ok else []):
+        ok &= int(host(dcls)[0, i]) == wc and host(boxes)[0, i].tolist() == wbox.tolist() and float(host(probs)[0, i]) == float(wp)
+    return bool(ok), dict(kind="postprocess", m=m, ratio=ratio, thr=thr)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=300)
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
-    kinds = [case_nms, case_proposals, case_roi, case_labels]
+    kinds = [case_nms, case_proposals, case_roi, case_labels, case_label_rois, case_postprocess]
     counts, failures = {}, []
     for i in range(args.cases):
         fn = kinds[i % len(kinds)]
