@@ -18,6 +18,12 @@ namespace frcnn {
 
 struct __align__(8) BoxI16 { short x1, y1, x2, y2; };
 
+constexpr int TOPK_THREADS = 1024;
+constexpr int TOPK_WARPS = TOPK_THREADS / 32;
+constexpr int TOPK_BITS = 11;                       // radix-select digit width
+constexpr int TOPK_BINS = 1 << TOPK_BITS;
+constexpr int TOPK_META = TOPK_BINS + 1;            // per image: [valid count, histogram of the keys' top 11 bits]
+
 __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ regr,
                                                      const float* __restrict__ cls, AnchorTable tab,
                                                      int rows, int cols, int n_per_image,
@@ -28,6 +34,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ r
   const int img = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = false;
+  unsigned digit = 0xffffffffu;
   if (i < n_per_image) {
     const size_t g = (size_t)img * n_per_image + i;
     const int a = i % tab.n;
@@ -74,16 +81,18 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ r
     }
     keys[g] = key;
     boxes[g] = b;
+    digit = valid ? (unsigned)(key >> (64 - TOPK_BITS)) : 0xffffffffu;
   }
+  // first pass of top-k's radix select, done here while the key is in a register: histogram of the top 11 bits
+  // (a handful of distinct digits per warp -> one aggregated atomic per digit)
+  int* meta = valid_count + (size_t)img * TOPK_META;
+  const unsigned peers = __match_any_sync(0xffffffffu, digit);
+  if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(meta + 1 + digit, __popc(peers));
   // number of valid anchors of the image (top-k needs it): one atomic per CTA
   const int nv = __syncthreads_count(valid);
-  if (threadIdx.x == 0 && nv) atomicAdd(valid_count + img, nv);
+  if (threadIdx.x == 0 && nv) atomicAdd(meta, nv);
 }
 
-constexpr int TOPK_THREADS = 1024;
-constexpr int TOPK_WARPS = TOPK_THREADS / 32;
-constexpr int TOPK_BITS = 11;                       // radix-select digit width
-constexpr int TOPK_BINS = 1 << TOPK_BITS;
 
 // block-wide inclusive scan of one int per thread (1024 threads); `warp_tot` is [TOPK_WARPS] shared
 __device__ __forceinline__ int block_inclusive_scan(int v, int* warp_tot) {
@@ -124,11 +133,12 @@ __device__ __forceinline__ int pad_slot(int e) { return e + e / E; }
 // still agree (always in the first pass) one histogram serves both.
 // Keys are fetched 8 per thread before any is consumed, which hides the L2 latency.
 constexpr int TOPK_U = 8;
-__device__ void radix_select2(const unsigned long long* __restrict__ keys, int n, int rank_a, int rank_b, bool use_b,
+__device__ void radix_select2(const unsigned long long* __restrict__ keys, const int* __restrict__ g_hist1, int n,
+                              int rank_a, int rank_b, bool use_b,
                               unsigned* hist /* [2][TOPK_BINS] */, int* warp_tot, unsigned long long* s_prefix /* [2] */,
                               int* s_need /* [2] */, int* s_done /* [2] */, unsigned long long& t_a,
                               unsigned long long& t_b) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   if (tid == 0) {
     s_prefix[0] = s_prefix[1] = 0ull;
     s_need[0] = rank_a; s_need[1] = rank_b;
@@ -143,6 +153,9 @@ __device__ void radix_select2(const unsigned long long* __restrict__ keys, int n
     const unsigned long long pa = s_prefix[0], pb = s_prefix[1];
     const bool da = s_done[0] != 0, db = s_done[1] != 0;
     const bool same = !da && !db && (hi == 64 || (pa >> hi) == (pb >> hi));   // identical histograms: build A's only
+    if (hi == 64) {                                  // first pass: decode_kernel already histogrammed the top bits
+      for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = (unsigned)__ldg(g_hist1 + i);
+    } else
     for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
       unsigned long long kk[TOPK_U];
 #pragma unroll
@@ -155,14 +168,8 @@ __device__ void radix_select2(const unsigned long long* __restrict__ keys, int n
         const unsigned long long key = kk[u];
         const bool in_a = !da && key != 0ull && (hi == 64 || (key >> hi) == (pa >> hi));
         const unsigned digit = (unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u));
-        if (hi == 64) {
-          // first pass: a handful of distinct digits per warp (sign + exponent bits) -> aggregate
-          const unsigned peers = __match_any_sync(0xffffffffu, in_a ? digit : 0xffffffffu);
-          if (in_a && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
-        } else {
-          if (in_a) atomicAdd(&hist[digit], 1u);     // later passes: few keys left and their digits are spread out
-          if (!db && !same && key != 0ull && (key >> hi) == (pb >> hi)) atomicAdd(&hist[TOPK_BINS + digit], 1u);
-        }
+        if (in_a) atomicAdd(&hist[digit], 1u);       // few keys are left after the first pass and their digits are spread out
+        if (!db && !same && key != 0ull && (key >> hi) == (pb >> hi)) atomicAdd(&hist[TOPK_BINS + digit], 1u);
       }
     }
     __syncthreads();
@@ -219,7 +226,8 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
 
   if (tid == 0) s_count = 0;
   __syncthreads();
-  const int n_valid = __ldg(valid_count + img);       // counted by decode_kernel
+  const int* meta = valid_count + (size_t)img * TOPK_META;
+  const int n_valid = __ldg(meta);                    // counted by decode_kernel
   const int m = min(k, n_valid);
   const int first = (int)((long long)part * k / splits);                       // ranks [first, last) belong to this CTA
   const int slice_end = (int)((long long)(part + 1) * k / splits);
@@ -231,14 +239,14 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
     const bool need_hi = first > 0, need_lo = last < n_valid;
     unsigned long long ta = 0ull, tb = 0ull;
     if (need_hi && need_lo) {
-      radix_select2(keys, n, first, last, true, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
+      radix_select2(keys, meta + 1, n, first, last, true, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
       t_hi = ta;
       t_lo = tb;
     } else if (need_hi) {
-      radix_select2(keys, n, first, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
+      radix_select2(keys, meta + 1, n, first, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
       t_hi = ta;
     } else if (need_lo) {
-      radix_select2(keys, n, last, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
+      radix_select2(keys, meta + 1, n, last, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
       t_lo = ta;
     }
   }
@@ -363,12 +371,12 @@ int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, 
   const size_t key_bytes = align_up((size_t)batch * n * sizeof(unsigned long long), 256);
   const size_t box_bytes = align_up((size_t)batch * n * sizeof(BoxI16), 256);
   void* ws = nullptr;
-  int rc = arena_get(h, stream, key_bytes + box_bytes + (size_t)batch * sizeof(int), &ws);
+  int rc = arena_get(h, stream, key_bytes + box_bytes + (size_t)batch * TOPK_META * sizeof(int), &ws);
   if (rc) return rc;
   auto* keys = reinterpret_cast<unsigned long long*>(ws);
   auto* boxes = reinterpret_cast<BoxI16*>(reinterpret_cast<char*>(ws) + key_bytes);
   int* valid_count = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + key_bytes + box_bytes);
-  FRCNN_CUDA(h, cudaMemsetAsync(valid_count, 0, (size_t)batch * sizeof(int), stream));
+  FRCNN_CUDA(h, cudaMemsetAsync(valid_count, 0, (size_t)batch * TOPK_META * sizeof(int), stream));
 
   dim3 grid((n + 255) / 256, batch);
   decode_kernel<<<grid, 256, 0, stream>>>(regr, cls, tab, rows, cols, n, keys, boxes,
