@@ -7,9 +7,12 @@
 // Forward (both modes): one CTA per (RoI, 256-channel block, image); a thread owns four
 // consecutive channels (128-bit loads/stores), walks the PxP outputs and streams them out with
 // evict-first stores.  The feature map (9.8 MB at 38x63x1024) stays L2-resident, the P*P*C
-// outputs (401 MB at N=2000) are the HBM stream.
+// outputs (401 MB at N=2000) are the HBM stream.  Values that two consecutive outputs share are
+// carried in registers instead of being fetched twice: the interpolated bottom row (or the right
+// taps, for crops taller than wide) in resize mode, the boundary row of two bins in max mode.
 //
-// Backward (both modes): cell-stationary gather, one warp per dX cell accumulating in registers.
+// Backward (both modes): cell-stationary gather, one warp per dX cell accumulating in registers
+// (four warps per cell, each a quarter of the RoIs, for small resize-mode launches).
 // Both walk RoIs in index order and, inside a RoI, bins in (ph, pw, tap) order, so every addition
 // into a given dX element happens in one fixed order: no atomics, bit-reproducible run to run.
 // (oracle/roi_oracle.py sums each RoI into a private crop first, like TF's slice-gradient +
