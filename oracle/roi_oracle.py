@@ -1,6 +1,6 @@
 """CPU oracle for the RoI layer (`RoiResizeConv`) -- TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED.  The reference layer (custom_layers.py:35-56) crops
+PARITY UNPINNED for the resize mode (the max mode is pinned, see below).  The reference layer (custom_layers.py:35-56) crops
 ``img[:, y1:y2, x1:x2, :]`` per RoI and calls ``tf.image.resize_images(crop,
 (P, P))`` of tensorflow==1.3.0 (requirements.txt:53), i.e. the legacy bilinear
 kernel with ``align_corners=False`` and no half-pixel offset.  TensorFlow is a
@@ -23,10 +23,13 @@ is `torch.nn.functional.grid_sample` on explicit legacy-coordinate grids
 (tests/test_oracle_roi.py, tolerance only).
 
 `mode="max"` (roi_max_*) is the north-star max-pool variant; the reference has
-no such layer, so its spec is defined here:  bin (ph,pw) of an h x w crop covers
-rows  y1 + floor(ph*h/P) .. y1 + ceil((ph+1)*h/P) - 1  (cols likewise); output
-is the max over the bin, argmax the flat ``y*W + x`` of the FIRST maximum in
-row-major scan; backward adds dY to dX[argmax].
+no such layer.  Its spec is the Fast R-CNN RoIPool:  bin (ph,pw) of an h x w crop
+covers rows  y1 + floor(ph*h/P) .. y1 + ceil((ph+1)*h/P) - 1  (cols likewise);
+output is the max over the bin, argmax the flat ``y*W + x`` of the FIRST maximum
+in row-major scan; backward adds dY to dX[argmax].  PINNED against an independent
+implementation: outputs equal ``torchvision.ops.roi_pool`` bit for bit (exclusive
+x2/y2 passed as inclusive ends, spatial_scale 1) and the backward equals its
+autograd on tie-rich inputs (tests/test_oracle_roi.py).
 
 Layouts: feat (H,W,C) f32 channels-last (batch index 0 of the Keras tensor),
 rois (N,4) integer [x1,y1,x2,y2] in feature cells with x2/y2 EXCLUDED from the

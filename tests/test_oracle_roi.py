@@ -61,3 +61,32 @@ def test_max_pool_spec():
     gout = rng.standard_normal(out.shape).astype(np.float32)
     dx = R.roi_max_bwd(gout, arg, feat.shape)
     assert abs(float(dx.sum()) - float(gout.sum())) < 1e-3
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_max_mode_is_torchvision_roi_pool(seed):
+    """Pins the max-pool variant (which the reference does not have) to an independent implementation: the oracle's
+    bins, outputs and arg-max rule are those of torchvision.ops.roi_pool (the Fast R-CNN RoIPool: hstart =
+    floor(ph*h/P), hend = ceil((ph+1)*h/P), first maximum in row-major order) once the exclusive x2/y2 of this
+    path are passed as inclusive ends.  Outputs bit for bit; the backward against torchvision's autograd, with
+    tie-rich features so that the arg-max rule is exercised."""
+    tv = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(seed)
+    for _ in range(25):
+        h, w, c, n = int(rng.integers(1, 40)), int(rng.integers(1, 64)), 3, 16
+        pool = int(rng.choice([1, 2, 3, 7, 9]))
+        feat = rng.standard_normal((h, w, c), dtype=np.float32)
+        if rng.random() < 0.5:
+            feat = np.round(feat * 2) / 2                                    # ties
+        x1, y1 = rng.integers(0, w, n), rng.integers(0, h, n)
+        rois = np.stack([x1, y1, np.minimum(w, x1 + 1 + rng.integers(0, w, n)), np.minimum(h, y1 + 1 + rng.integers(0, h, n))], 1).astype(np.int16)
+        out, arg = R.roi_max_fwd(feat, rois, pool)
+        t = torch.from_numpy(feat).permute(2, 0, 1)[None].clone().requires_grad_(True)
+        boxes = torch.tensor([[0, a, b, c2 - 1, d - 1] for a, b, c2, d in rois.tolist()], dtype=torch.float32)
+        want = tv.ops.roi_pool(t, boxes, output_size=pool, spatial_scale=1.0)                 # (K, C, P, P)
+        assert np.array_equal(out, want.detach().permute(0, 2, 3, 1).numpy())
+        g = rng.standard_normal(out.shape, dtype=np.float32)
+        want.backward(torch.from_numpy(g).permute(0, 3, 1, 2))
+        got = R.roi_max_bwd(g, arg, feat.shape)
+        ref = t.grad[0].permute(1, 2, 0).numpy()
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, float(np.abs(ref).max()))
