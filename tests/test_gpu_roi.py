@@ -176,3 +176,20 @@ def test_roi_layer_dropin_and_autograd():
     assert np.array_equal(mlayer([feat, rois])[0], R.roi_max_fwd(feat[0], rois[0], 7)[0])
     with pytest.raises(ValueError):
         layer([feat, rois[:, :3]])
+
+
+def test_roi_max_full_size_equals_torchvision_roi_pool(ops):
+    """C5 shape (38x63x1024, 2000 RoIs): the CUDA max-mode forward equals torchvision.ops.roi_pool's CUDA kernel bit for
+    bit (an independent implementation of the same RoIPool spec), and the arg-max gathers those outputs."""
+    import torch
+    tv = pytest.importorskip("torchvision")
+    from faster_rcnn_b200 import synth
+    h, w, c, n = 38, 63, 1024, 2000
+    torch.manual_seed(1)
+    feat = torch.randn((1, h, w, c), device="cuda")
+    rois_np = synth.random_rois(n, h, w, 5)
+    out, arg = ops.roi_forward(feat, dev(rois_np[None]), 7, "max")
+    boxes = torch.tensor(np.concatenate([np.zeros((n, 1)), rois_np[:, :2], rois_np[:, 2:] - 1], axis=1), dtype=torch.float32, device="cuda")
+    want = tv.ops.roi_pool(feat.permute(0, 3, 1, 2).contiguous(), boxes, output_size=7, spatial_scale=1.0)     # (N, C, 7, 7)
+    assert torch.equal(out[0], want.permute(0, 2, 3, 1))
+    assert torch.equal(torch.gather(feat.reshape(h * w, c), 0, arg.reshape(-1, c).long()).reshape(out.shape), out)
