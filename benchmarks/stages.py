@@ -129,6 +129,33 @@ def main():
                 del gout, arg
         del feat
 
+    # ---- library comparison for the max mode: torchvision.ops.roi_pool (NCHW, atomics in the backward) on the same RoIs
+    if want("tv_roi_pool"):
+        try:
+            import torchvision
+        except ImportError:
+            torchvision = None
+        for tag, n_rois, batch in (("C1 320 rois", 320, 64), ("C5 2000 rois", 2000, 1), ("C5 2000 rois", 2000, 8)):
+            if torchvision is None:
+                break
+            h, w, c, p = 38, 63, 1024, 7
+            feat = torch.randn((batch, c, h, w), device="cuda", requires_grad=True)
+            r = np.stack([synth.random_rois(n_rois, h, w, 7 + i) for i in range(batch)]).astype(np.float32)
+            idx = np.repeat(np.arange(batch, dtype=np.float32), n_rois)[:, None]
+            boxes = dev(np.concatenate([idx, r.reshape(-1, 4)[:, :2], r.reshape(-1, 4)[:, 2:] - 1], axis=1))
+            nbytes = 4 * batch * h * w * c + 8 * batch * n_rois + 2 * 4 * batch * n_rois * p * p * c
+            ms = timeit(lambda: torchvision.ops.roi_pool(feat, boxes, p, 1.0), max(3, args.iters // 4), 2)
+            rec("tv_roi_pool_fwd", "%s b%d (torchvision %s, library kernel)" % (tag, batch, torchvision.__version__), ms, batch, nbytes)
+            out = torchvision.ops.roi_pool(feat, boxes, p, 1.0)
+            g = torch.randn_like(out)
+
+            def bwd():
+                feat.grad = None
+                out.backward(g, retain_graph=True)
+            ms = timeit(bwd, max(3, args.iters // 4), 2)
+            rec("tv_roi_pool_bwd", "%s b%d (torchvision, atomics)" % (tag, batch), ms, batch, nbytes)
+            del feat, out, g
+
     # ---- device-resident pipeline (decode -> top-k -> NMS -> pad -> RoI layer), eager launches vs one CUDA graph ------
     if want("pipeline"):
         from faster_rcnn_b200.pipeline import ProposalRoiPipeline
