@@ -754,7 +754,7 @@ int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
     int cpb = blocks128 >= 8 ? 8 : (blocks128 >= 4 ? 4 : (blocks128 >= 2 ? 2 : 1));
     // resize mode, fewer than ~4 waves of warps and enough RoI chunks to share: four warps per cell (RS = 4)
     const long long cell_warps = (long long)H * W * batch * ((blocks128 + cpb - 1) / cpb);
-    const bool split = mode == FRCNN_ROI_RESIZE && P <= 8 && cell_warps < 4LL * h->sm_count * 24 && N >= 256;
+    const bool split = mode == FRCNN_ROI_RESIZE && P <= 8 && cell_warps < 8LL * h->sm_count * 24 && N >= 256;
     if (!split && cpb == 8 && (long long)H * W * batch < 2LL * h->sm_count * 32) cpb = 4;
     const int cells_per_cta = split ? 1 : CW_WARPS;        // split: one cell per 4-warp CTA
     dim3 grid((H * W + cells_per_cta - 1) / cells_per_cta, (blocks128 + cpb - 1) / cpb, batch);
