@@ -245,3 +245,39 @@ def test_shapes_value_objects_match_the_reference(ref):
     for args in ((456, 264, 128, 128), (8, 8, 91, 181), (0, 0, 5, 11)):
         assert np.array_equal(M.Box.from_center_dims_int(*args).corners, S.Box.from_center_dims_int(*args).corners)
     assert np.array_equal(M.Box.from_corners([1, 2, 3, 4]).corners, S.Box.from_corners([1, 2, 3, 4]).corners)
+
+
+def test_oracle_equals_reference_on_drawn_inputs(ref):
+    """hypothesis-drawn boxes, scores, ground truth and image sizes: NMS picks, IoU matrices and RPN labels of the oracle
+    equal the live reference bit for bit (tie-free scores: the reference's argsort is only defined there)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(1, 300), st.sampled_from([0.3, 0.5, 0.7]), st.integers(1, 64),
+           st.integers(1, 12), st.sampled_from([(1000, 600), (800, 600), (600, 904), (333, 500)]))
+    def run(seed, n, thresh, max_boxes, n_gt, wh):
+        rng = np.random.default_rng(seed)
+        xy = rng.integers(0, 60, (n, 2))
+        boxes = np.concatenate([xy, xy + rng.integers(0, 40, (n, 2))], axis=1).astype(np.int16)
+        probs = ((rng.permutation(n) + 0.5) / n).astype(np.float32)
+        with ref_loader.quiet():
+            wb, wp = ref.det_util.nms(boxes, probs, overlap_thresh=thresh, max_boxes=max_boxes)
+        pick = O.greedy_nms(boxes, probs, thresh, max_boxes)
+        assert np.array_equal(boxes[pick], wb) and np.array_equal(probs[pick], wp)
+        a = (rng.integers(0, 200, (n, 4)) + np.array([0, 0, 200, 200])).astype(np.float32)
+        g = (rng.integers(0, 200, (n_gt, 4)) + np.array([0, 0, 200, 200])).astype(np.float32)
+        assert np.array_equal(O.iou_matrix(a, g), ref.util.cross_ious(a, g))
+        w, h = wh
+        gts = synth.gt_boxes(n_gt, w, h, seed % 100000)
+        img = _ref_image(ref, 'drawn', w, h, gts)
+        dims = O.anchor_table([128, 256, 512])
+        mgr = ref.rpn_util.RpnTrainingManager(O.conv_dims_resnet, 16, preprocess_func=None, anchor_dims=dims)
+        with ref_loader.quiet():
+            mgr._process(img)
+        want = mgr._cache[img.cache_key]
+        rows, cols = O.conv_dims_resnet(h, w)
+        cu, ip, bb = O.label_anchors(w, h, np.array([x[1:] for x in gts], np.float32), rows, cols, dims, 16)
+        assert np.array_equal(cu, want['can_use']) and np.array_equal(ip, want['is_pos']) and np.array_equal(bb, want['bbreg_targets'])
+
+    run()
