@@ -23,63 +23,11 @@
 //   top = tl + (tr-tl)*lx; bottom = bl + (br-bl)*lx; out = top + (bottom-top)*ly
 // MAX mode: bin rows y1+floor(ph*h/P) .. y1+ceil((ph+1)*h/P)-1, first maximum in row-major scan.
 // This TU is compiled with -fmad=false so that a*b+c keeps two roundings like the CPU oracle.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "roi_common.cuh"
 
 namespace frcnn {
-
-struct Crop { int x1, y1, w, h; };   // clipped to the map; w,h <= 0 means empty
-
-__device__ __forceinline__ Crop load_crop(const void* rois, int dtype, size_t idx, int W, int H) {
-  int x1, y1, x2, y2;
-  if (dtype == FRCNN_ROI_I16) {
-    const short* p = reinterpret_cast<const short*>(rois) + idx * 4;
-    x1 = p[0]; y1 = p[1]; x2 = p[2]; y2 = p[3];
-  } else if (dtype == FRCNN_ROI_I32) {
-    const int* p = reinterpret_cast<const int*>(rois) + idx * 4;
-    x1 = p[0]; y1 = p[1]; x2 = p[2]; y2 = p[3];
-  } else {
-    const float* p = reinterpret_cast<const float*>(rois) + idx * 4;
-    x1 = (int)p[0]; y1 = (int)p[1]; x2 = (int)p[2]; y2 = (int)p[3];   // K.cast(.., 'int32') truncates
-  }
-  x1 = max(x1, 0); y1 = max(y1, 0); x2 = min(x2, W); y2 = min(y2, H);
-  return Crop{x1, y1, x2 - x1, y2 - y1};
-}
-
-struct Tap { int lo, hi; float lerp; };
-__device__ __forceinline__ Tap axis_tap(int i, float scale, int in_size) {
-  const float src = (float)i * scale;
-  Tap t;
-  t.lo = (int)src;
-  t.hi = min(t.lo + 1, in_size - 1);
-  t.lerp = src - (float)t.lo;
-  return t;
-}
-
-// Blackwell packed fp32 (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2): two IEEE-rounded float32 results per
-// instruction on an aligned register pair, i.e. half the issue slots for the same arithmetic.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 
 // a + (b - a) * t with three roundings per element like numpy / TF's CPU kernel.  The subtraction and the product are
 // packed; the final addition stays scalar because ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (a
@@ -740,10 +688,19 @@ int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
   return FRCNN_OK;
 }
 
+bool roi_bwd_blk_eligible(int mode, int H, int W, int C, int N, int P);
+int launch_roi_bwd_blk(frcnn_handle*, cudaStream_t, int, const float*, const void*, int, const int32_t*, int, int, int,
+                       int, int, int, float*);
+
 int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* gout, const void* rois, int dtype,
                    const int32_t* argmax, int H, int W, int C, int N, int P, int batch, float* gfeat) {
   const bool aligned = (reinterpret_cast<uintptr_t>(gout) % 16 == 0) && (reinterpret_cast<uintptr_t>(gfeat) % 16 == 0) &&
                        (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0);
+  {
+    const char* impl = getenv("FRCNN_BWD_IMPL");          // "cell": force the round-1 cell-stationary kernels (A/B runs)
+    if (aligned && roi_bwd_blk_eligible(mode, H, W, C, N, P) && !(impl && impl[0] == 'c'))
+      return launch_roi_bwd_blk(h, stream, mode, gout, rois, dtype, argmax, H, W, C, N, P, batch, gfeat);
+  }
   if (C % 4 == 0 && aligned && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768) {
     int4 *crops = nullptr, *taps = nullptr;
     int rc = build_tables(h, stream, mode, rois, dtype, batch * N, W, H, P, &crops, &taps);

@@ -3,7 +3,8 @@
 resize mode: forward bit-exact (same float32 op order, no FMA); backward within 1e-5 relative
 (the oracle sums each RoI into a private crop first like TF's slice-gradient + AddN, the kernel adds
 taps straight into the owned tile -- a different but fixed float32 summation order).
-max mode: outputs, argmax and backward bit-exact."""
+max mode: outputs and argmax bit-exact; backward bit-exact while one warp walks a block's list (fewer than 256 RoIs
+per image, or launches large enough to need no slicing), 1e-5 relative (like the resize mode) when the list is sliced across warps."""
 import numpy as np
 import pytest
 
@@ -118,7 +119,11 @@ def test_roi_backward_kernel_variants(ops, b, h, w, c, n, pool):
         assert np.abs(g[i] - want).max() <= 1e-5 * np.abs(want).max()
         wout, warg = R.roi_max_fwd(feat[i], rois[i], pool)
         assert np.array_equal(host(out)[i], wout) and np.array_equal(host(arg)[i], warg)
-        assert np.array_equal(gm[i], R.roi_max_bwd(gout[i], warg, (h, w, c)))
+        wm = R.roi_max_bwd(gout[i], warg, (h, w, c))
+        if n < 256:                       # one warp walks a block's whole list: the oracle's (roi, ph, pw) order, bit for bit
+            assert np.array_equal(gm[i], wm)
+        else:                             # sliced lists: partial sums are added in slice order (fixed, but re-associated)
+            assert np.abs(gm[i] - wm).max() <= 1e-5 * np.abs(wm).max()
 
 
 def test_roi_full_size_properties(ops):
