@@ -27,13 +27,17 @@
 namespace frcnn {
 
 constexpr int BLK = 2;                       // block edge in cells
-constexpr int PLAN_THREADS = 256;
 constexpr unsigned ENT_MASK_SHIFT = 28;      // entry word = dY row index | cell mask << 28
 constexpr unsigned ENT_IDX_MASK = (1u << ENT_MASK_SHIFT) - 1u;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_if(void* smem_dst, const void* gsrc, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }"
+               ::"r"(s), "l"(gsrc), "r"((int)pred) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -109,13 +113,12 @@ __constant__ unsigned short c_div_magic[9] = {0, 512, 256, 171, 128, 103, 86, 74
 // with one lane per RoI left ~5 of 32 lanes busy and was 4x slower.
 constexpr int PLAN_ROUND = 256;              // RoIs per queue round and warp
 
-template <int MODE>
-__global__ void __launch_bounds__(PLAN_THREADS)
+template <int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 roi_bwd_plan_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, int H, int W, int P, int blocks_y,
                     int blocks_x, unsigned capacity, const uint8_t* __restrict__ ymask,
                     const uint8_t* __restrict__ xmask, unsigned* __restrict__ counter, int2* __restrict__ blk_tab,
                     unsigned* __restrict__ ent_idx, float4* __restrict__ ent_w) {
-  constexpr int WARPS = PLAN_THREADS / 32;
   __shared__ int s_wtot[WARPS];
   __shared__ unsigned s_wbase[WARPS];
   __shared__ unsigned s_qroi[WARPS][PLAN_ROUND];            // RoI index | my << 16 | mx << 24
@@ -291,15 +294,58 @@ roi_bwd_blk_kernel(const float* __restrict__ gout, const int* __restrict__ argma
       cp_async4(enti + (b & 1) * 32 + lane, ei + e);
     }
   };
-  auto issue_row = [&](int i) {
-    if (i < n) {
-      const unsigned row = enti[((i >> 5) & 1) * 32 + (i & 31)] & ENT_IDX_MASK;
-      const size_t off = (size_t)row * C;
-      float4* slot = ring + (i & (D - 1)) * S::ROW_F4 + lane;
+  // request the dY (and arg-max) row of list entry i into ring slot `s`; predicated, not branched: entries past the
+  // end of the list are simply not loaded (the stale index word they would use is never dereferenced)
+  auto issue_row = [&](int i, int s) {
+    const unsigned row = enti[i & 63] & ENT_IDX_MASK;  // entry buffers: 2 x 32 entries back to back
+    const size_t off = (size_t)row * C;
+    const bool p = i < n;
+    float4* slot = ring + s * S::ROW_F4 + lane;
+#pragma unroll
+    for (int j = 0; j < CPB; ++j) {
+      cp_async16_if(slot + j * 32, g_img + off + coff[j], p);
+      if (MODE == FRCNN_ROI_MAX) cp_async16_if(slot + (CPB + j) * 32, a_img + off + coff[j], p);
+    }
+  };
+  // add list entry i (its rows sit in ring slot `s`) into the four cells
+  auto consume = [&](int i, int s) {
+    const float4* slot = ring + s * S::ROW_F4 + lane;
+    if (MODE == FRCNN_ROI_RESIZE) {
+      const float4 w = entw[i & 63];
+      const unsigned mask = enti[i & 63] >> ENT_MASK_SHIFT;
+      unsigned long long g2[CPB][2];
 #pragma unroll
       for (int j = 0; j < CPB; ++j) {
-        cp_async16(slot + j * 32, g_img + off + coff[j]);
-        if (MODE == FRCNN_ROI_MAX) cp_async16(slot + (CPB + j) * 32, a_img + off + coff[j]);
+        const float4 g = slot[j * 32];
+        g2[j][0] = pack2(g.x, g.y);
+        g2[j][1] = pack2(g.z, g.w);
+      }
+      // the tap weight wy*wx was formed by the plan kernel; one packed FMA per element pair and cell
+#define FRCNN_BLK_ACCUM(Q, WV)                                                                  \
+  if (mask & (1u << (Q))) {                                                                      \
+    const unsigned long long ww = pack2(WV, WV);                                                 \
+    _Pragma("unroll") for (int j = 0; j < CPB; ++j) {                                            \
+      unpack2(fma2(g2[j][0], ww, pack2(acc[Q][j].x, acc[Q][j].y)), acc[Q][j].x, acc[Q][j].y);     \
+      unpack2(fma2(g2[j][1], ww, pack2(acc[Q][j].z, acc[Q][j].w)), acc[Q][j].z, acc[Q][j].w);     \
+    }                                                                                            \
+  }
+      FRCNN_BLK_ACCUM(0, w.x)
+      FRCNN_BLK_ACCUM(1, w.y)
+      FRCNN_BLK_ACCUM(2, w.z)
+      FRCNN_BLK_ACCUM(3, w.w)
+#undef FRCNN_BLK_ACCUM
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPB; ++j) {
+        const float4 g = slot[j * 32];
+        const int4 a = *reinterpret_cast<const int4*>(slot + (CPB + j) * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (a.x == cellid[q]) acc[q][j].x += g.x;
+          if (a.y == cellid[q]) acc[q][j].y += g.y;
+          if (a.z == cellid[q]) acc[q][j].z += g.z;
+          if (a.w == cellid[q]) acc[q][j].w += g.w;
+        }
       }
     }
   };
@@ -313,58 +359,32 @@ roi_bwd_blk_kernel(const float* __restrict__ gout, const int* __restrict__ argma
     cp_async_commit();
 #pragma unroll
     for (int s = 0; s < D; ++s) {
-      issue_row(s);
+      issue_row(s, s);
       cp_async_commit();
     }
-    for (int i = 0; i < n; ++i) {
-      cp_async_wait<D - 1>();                        // row i (and every older group, entry batches included) has landed
-      if ((i & 31) == 32 - D) __syncwarp();          // the next entry batch becomes visible across lanes before issue_row reads it
-      const int es = ((i >> 5) & 1) * 32 + (i & 31);
-      const float4* slot = ring + (i & (D - 1)) * S::ROW_F4 + lane;
-      if (MODE == FRCNN_ROI_RESIZE) {
-        const float4 w = entw[es];
-        const unsigned mask = enti[es] >> ENT_MASK_SHIFT;
-        unsigned long long g2[CPB][2];
+    // groups of D entries: ring slots and the batch hand-over points are compile-time positions inside a group.
+    // Entry batch i/32 + 1 was committed >= D groups before the first issue_row that reads it (D <= 16), so it
+    // has landed for the copying lane; the __syncwarp makes it visible to the other lanes.
+    int i0 = 0;
+    for (; i0 + D <= n; i0 += D) {
+      const bool handover = (i0 & 31) == 32 - D;      // this group ends a batch of 32 entries
+      if (handover) __syncwarp();
 #pragma unroll
-        for (int j = 0; j < CPB; ++j) {
-          const float4 g = slot[j * 32];
-          g2[j][0] = pack2(g.x, g.y);
-          g2[j][1] = pack2(g.z, g.w);
+      for (int u = 0; u < D; ++u) {
+        cp_async_wait<D - 1>();                       // row i0 + u has landed
+        consume(i0 + u, u);
+        if (u == D - 1 && handover) {                 // batch i0/32 is consumed: its buffer takes batch i0/32 + 2
+          __syncwarp();
+          fetch_batch((i0 >> 5) + 2);
         }
-        // the tap weight wy*wx was formed by the plan kernel; one packed FMA per element pair and cell
-#define FRCNN_BLK_ACCUM(Q, WV)                                                                  \
-  if (mask & (1u << (Q))) {                                                                      \
-    const unsigned long long ww = pack2(WV, WV);                                                 \
-    _Pragma("unroll") for (int j = 0; j < CPB; ++j) {                                            \
-      unpack2(fma2(g2[j][0], ww, pack2(acc[Q][j].x, acc[Q][j].y)), acc[Q][j].x, acc[Q][j].y);     \
-      unpack2(fma2(g2[j][1], ww, pack2(acc[Q][j].z, acc[Q][j].w)), acc[Q][j].z, acc[Q][j].w);     \
-    }                                                                                            \
-  }
-        FRCNN_BLK_ACCUM(0, w.x)
-        FRCNN_BLK_ACCUM(1, w.y)
-        FRCNN_BLK_ACCUM(2, w.z)
-        FRCNN_BLK_ACCUM(3, w.w)
-#undef FRCNN_BLK_ACCUM
-      } else {
-#pragma unroll
-        for (int j = 0; j < CPB; ++j) {
-          const float4 g = slot[j * 32];
-          const int4 a = *reinterpret_cast<const int4*>(slot + (CPB + j) * 32);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (a.x == cellid[q]) acc[q][j].x += g.x;
-            if (a.y == cellid[q]) acc[q][j].y += g.y;
-            if (a.z == cellid[q]) acc[q][j].z += g.z;
-            if (a.w == cellid[q]) acc[q][j].w += g.w;
-          }
-        }
+        issue_row(i0 + u + D, u);
+        cp_async_commit();
       }
-      if ((i & 31) == 31) {                          // batch i/32 is consumed: its buffer takes batch i/32 + 2
-        __syncwarp();
-        fetch_batch((i >> 5) + 2);
-      }
-      issue_row(i + D);
-      cp_async_commit();
+    }
+    if (i0 < n) {                                     // ragged tail: fewer than D entries, everything already requested
+      cp_async_wait<0>();
+      if ((i0 & 31) == 32 - D) __syncwarp();
+      for (int i = i0; i < n; ++i) consume(i, i & (D - 1));
     }
     cp_async_wait<0>();
   }
@@ -469,17 +489,19 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   FRCNN_CUDA(h, cudaMemsetAsync(p_cnt, 0, 4, stream));
   dim3 mgrid((n_pad + 255) / 256, blocks_y + blocks_x, batch), pgrid(n_blocks, batch);
   uint8_t *ym = static_cast<uint8_t*>(p_ym), *xm = static_cast<uint8_t*>(p_xm);
+  // plan CTAs: 8 warps sweep 2000 RoIs in one queue round each; short RoI lists take smaller CTAs (38912 of them at C1 x 64)
+#define FRCNN_PLAN(MODE, WARPS)                                                                                     \
+  roi_bwd_plan_kernel<MODE, WARPS><<<pgrid, WARPS * 32, 0, stream>>>(                                                \
+      rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, (unsigned)cap, ym, xm, static_cast<unsigned*>(p_cnt),       \
+      static_cast<int2*>(p_tab), static_cast<unsigned*>(p_idx), static_cast<float4*>(p_w))
   if (mode == FRCNN_ROI_RESIZE) {
     roi_bwd_mask_kernel<FRCNN_ROI_RESIZE><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
-    roi_bwd_plan_kernel<FRCNN_ROI_RESIZE><<<pgrid, PLAN_THREADS, 0, stream>>>(
-        rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, (unsigned)cap, ym, xm, static_cast<unsigned*>(p_cnt),
-        static_cast<int2*>(p_tab), static_cast<unsigned*>(p_idx), static_cast<float4*>(p_w));
+    if (N > 1024) FRCNN_PLAN(FRCNN_ROI_RESIZE, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_RESIZE, 4); else FRCNN_PLAN(FRCNN_ROI_RESIZE, 2);
   } else {
     roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
-    roi_bwd_plan_kernel<FRCNN_ROI_MAX><<<pgrid, PLAN_THREADS, 0, stream>>>(
-        rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, (unsigned)cap, ym, xm, static_cast<unsigned*>(p_cnt),
-        static_cast<int2*>(p_tab), static_cast<unsigned*>(p_idx), nullptr);
+    if (N > 1024) FRCNN_PLAN(FRCNN_ROI_MAX, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_MAX, 4); else FRCNN_PLAN(FRCNN_ROI_MAX, 2);
   }
+#undef FRCNN_PLAN
   FRCNN_LAUNCH_CHECK(h, "roi_bwd_mask_kernel");
   FRCNN_LAUNCH_CHECK(h, "roi_bwd_plan_kernel");
 
@@ -500,6 +522,11 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   const long long units = (long long)n_blocks * batch * slabs;
   const long long want = 4LL * 24 * h->sm_count;
   int parts = units >= want ? 1 : (units * 2 >= want ? 2 : (units * 4 >= want ? 4 : 8));
+  // long lists are also sliced in large launches: the eight warps of a CTA then work on 8 / parts blocks in equal
+  // shares instead of on eight blocks of unequal length (C5 x 8: 0.77 -> 0.63 ms with four slices)
+  const long long avg_list = (long long)N * P * P * (mode == FRCNN_ROI_MAX ? 3 : 2) / n_blocks;
+  if (parts < 4 && avg_list >= 256) parts = 4;
+  else if (parts < 2 && avg_list >= 128) parts = 2;
   if (N < 256) parts = 1;                              // short lists: one warp walks the whole list (reference order)
   parts = env_int("FRCNN_BWD_PARTS", parts);
   const int2* tab = static_cast<int2*>(p_tab);
