@@ -1,13 +1,12 @@
 """CPU oracle for the RoI layer (`RoiResizeConv`) -- TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED for the resize mode (the max mode is pinned, see below).  The reference layer (custom_layers.py:35-56) crops
-``img[:, y1:y2, x1:x2, :]`` per RoI and calls ``tf.image.resize_images(crop,
-(P, P))`` of tensorflow==1.3.0 (requirements.txt:53), i.e. the legacy bilinear
-kernel with ``align_corners=False`` and no half-pixel offset.  TensorFlow is a
-third-party dependency that is neither vendored under /root/reference nor
-installable here, and the reference's only tests for this layer are golden
-``.h5`` files that are missing (.MISSING_LARGE_BLOBS).  This file therefore
-restates the *published* TF-1.x algorithm (core/kernels/resize_bilinear_op.cc):
+Resize mode -- pinned through an independent executable implementation.  The reference layer
+(custom_layers.py:35-56) crops ``img[:, y1:y2, x1:x2, :]`` per RoI and calls
+``tf.image.resize_images(crop, (P, P))`` of tensorflow==1.3.0 (requirements.txt:53), i.e. the legacy bilinear
+kernel with ``align_corners=False`` and no half-pixel offset.  TensorFlow is a third-party dependency that is
+neither vendored under /root/reference nor installable here, and the reference's only tests for this layer are
+golden ``.h5`` files that are missing (.MISSING_LARGE_BLOBS).  This file restates the *published* TF-1.x
+algorithm (core/kernels/resize_bilinear_op.cc):
 
     scale = in_size / float(out_size)            (float32)
     src   = out_index * scale                    (float32)
@@ -18,9 +17,19 @@ restates the *published* TF-1.x algorithm (core/kernels/resize_bilinear_op.cc):
 
 and ResizeBilinearGrad (taps scattered in the order TL, TR, BL, BR with weights
 (1-ly)(1-lx), (1-ly)lx, ly(1-lx), ly*lx), followed by the zero-padded slice
-gradient and an AddN over RoIs in index order.  The cross-check available here
-is `torch.nn.functional.grid_sample` on explicit legacy-coordinate grids
-(tests/test_oracle_roi.py, tolerance only).
+gradient and an AddN over RoIs in index order.
+
+THE PIN (tests/test_oracle_roi.py, fixtures tests/golden/resize_bilinear_cv2dnn.npz made by
+tests/golden/make_golden_resize.py): OpenCV 4.13's cv2.dnn runs a real TensorFlow GraphDef holding the
+``ResizeBilinear`` op (align_corners=false) -- an implementation of exactly this op written by other people.
+`_axis_taps` (coordinates, border clamp, lerp weights) put through OpenCV's tap expression
+(`resize_bilinear_opencv_form`) reproduces cv2.dnn BIT FOR BIT on every fixture and on live random crops, so the
+sampling geometry is pinned exactly.  What remains restated is the association of the final four-tap
+combination (TF: top/bottom lerps as above; OpenCV: a + ly(b-a) + lx((c-a) + ly(d-c-b+a))), which moves results
+by float32 rounding only: `roi_resize_fwd` differs from cv2.dnn by <= 4 ulp-of-the-largest-tap, counted in the
+test.  The backward is the exact adjoint of the forward (tests/test_properties.py), so the same taps pin it up
+to summation order.  A second, tolerance-only cross-check is `torch.nn.functional.grid_sample` on explicit
+legacy-coordinate grids.
 
 `mode="max"` (roi_max_*) is the north-star max-pool variant; the reference has
 no such layer.  Its spec is the Fast R-CNN RoIPool:  bin (ph,pw) of an h x w crop
@@ -46,6 +55,20 @@ def _axis_taps(in_size, out_size):
     hi = np.minimum(lo + 1, in_size - 1)
     lerp = (src - lo.astype(np.float32)).astype(np.float32)
     return lo, hi, lerp
+
+
+def resize_bilinear_opencv_form(crop, pool):
+    """The taps of `_axis_taps` combined with OpenCV's expression (modules/dnn/src/layers/resize_layer.cpp, bilinear):
+    out = a + ly*(b - a) + lx*((c - a) + ly*(((d - c) - b) + a)), a/b = rows lo/hi at column lo, c/d at column hi.
+    Equals cv2.dnn's TF-ResizeBilinear bit for bit -- this is how the taps are pinned (see the header)."""
+    crop = np.asarray(crop, dtype=np.float32)
+    h, w = crop.shape[:2]
+    ylo, yhi, ly = _axis_taps(h, pool)
+    xlo, xhi, lx = _axis_taps(w, pool)
+    a, b = crop[ylo][:, xlo], crop[yhi][:, xlo]
+    c, d = crop[ylo][:, xhi], crop[yhi][:, xhi]
+    lyb, lxb = ly[:, None, None], lx[None, :, None]
+    return (a + lyb * (b - a)) + lxb * ((c - a) + lyb * (((d - c) - b) + a))
 
 
 def roi_resize_fwd(feat, rois, pool):

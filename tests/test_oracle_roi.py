@@ -1,12 +1,63 @@
-"""Cross-checks the RoI-layer oracle (parity unpinned: TensorFlow 1.3 is unavailable) against an independent
-formulation: torch.nn.functional.grid_sample on explicit legacy-coordinate grids (tolerance only), and checks
-its backward against torch autograd of that formulation.  CPU only."""
+"""Pins the RoI-layer oracle.  Resize mode: TensorFlow 1.3 is unavailable, so the TF `ResizeBilinear` op is executed
+by an independent implementation, OpenCV's cv2.dnn TensorFlow importer (fixtures + live): the oracle's taps reproduce
+it bit for bit, its TF-form output to a few ulp.  Also torch.nn.functional.grid_sample on explicit legacy-coordinate
+grids (tolerance only) with torch autograd for the backward.  Max mode: torchvision.ops.roi_pool.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
 from oracle import roi_oracle as R
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_bilinear_cv2dnn.npz")
+
+
+def _check_against_tf_resize_bilinear(x, y_cv2, pool):
+    """x (h,w,c) crop, y_cv2 = cv2.dnn's TF ResizeBilinear of it.  Returns the worst deviation of the oracle's TF-form
+    output in units of one float32 ulp of the largest tap magnitude."""
+    # (1) same taps, OpenCV's association of the four-tap sum: bit for bit
+    assert np.array_equal(R.resize_bilinear_opencv_form(x, pool), y_cv2)
+    # (2) TF's association (the oracle proper): float32 rounding only
+    h, w = x.shape[:2]
+    got = R.roi_resize_fwd(x, np.array([[0, 0, w, h]]), pool)[0]
+    ulp = np.spacing(np.float32(np.abs(x).max()))
+    return float(np.abs(got - y_cv2).max() / ulp)
+
+
+def test_resize_taps_pinned_by_cv2dnn_tensorflow_importer_golden():
+    """Fixtures from tests/golden/make_golden_resize.py: a hand-encoded TensorFlow GraphDef with the ResizeBilinear op
+    (align_corners=false) run by cv2.dnn 4.13 on crops from 1x1 to 38x63, pool 7 and 3."""
+    z = np.load(GOLDEN)
+    keys = sorted(k for k in z.files if k.startswith("x_"))
+    assert len(keys) == 32
+    worst, exact = 0.0, 0
+    for k in keys:
+        pool = int(k.rsplit("_", 1)[1])
+        dev = _check_against_tf_resize_bilinear(z[k], z["y" + k[1:]], pool)
+        worst, exact = max(worst, dev), exact + (dev == 0.0)
+    assert worst <= 4.0, worst            # tolerance: 4 ulp of the largest tap (observed 2.0); 17 of 32 cases are exact
+    assert exact >= 4                     # 1x1 / 7x7 / integer-ratio crops have no rounding at all
+
+
+def test_resize_taps_pinned_by_cv2dnn_tensorflow_importer_live():
+    """The same check against cv2.dnn run here, on every crop size the C1 / C5 proposals produce (1..24 cells per
+    side) plus the full map."""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "dnn"):
+        pytest.skip("cv2 without dnn")
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_resize import cv2_resize_bilinear
+    rng = np.random.default_rng(5)
+    sizes = [(h, w) for h in range(1, 25) for w in (1, 2, 3, 5, 7, 8, 11, 14, 17, 24)] + [(38, 63), (37, 62), (38, 94)]
+    worst = 0.0
+    for h, w in sizes:
+        x = rng.standard_normal((h, w, 3), dtype=np.float32)
+        worst = max(worst, _check_against_tf_resize_bilinear(x, cv2_resize_bilinear(x, 7), 7))
+    assert worst <= 4.0, worst
 
 
 def _torch_resize(feat, rois, pool):
