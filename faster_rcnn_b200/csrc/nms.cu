@@ -167,6 +167,14 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
   } else {
     int m = 1;
     while (m < n) m <<= 1;
+    if (m > buf_elems) {
+      // More than FRCNN_NMS_MAX_UNSORTED candidates that are NOT strictly descending (ties count): the power-of-two
+      // sort buffer does not fit.  Fail safe instead of overrunning shared memory: keep_count = -1, nothing kept.
+      // Every CTA of a cluster sees the same scores and takes this exit together.
+      if (tid == 0 && rank == 0) keep_count[img] = -1;
+      for (int i = tid; i < max_boxes && rank == 0; i += NMS_THREADS) keep_index[(size_t)img * max_boxes + i] = -1;
+      return;
+    }
     for (int i = tid; i < m; i += NMS_THREADS)
       buf[i] = (i < n) ? (((unsigned long long)mono_key(scores[i]) << 32) | (unsigned)i) : 0ull;
     // padding keys are 0: mono_key() of any real score is >= 1, so padding sorts last

@@ -172,9 +172,10 @@ def label_rois(rois, gt, gt_cls, n_gt, n_classes, n_roi=None):
     return out_rois, out_cls, out_bbreg, src, count
 
 
-def roi_forward(feat, rois, pool, mode="resize", out=None):
+def roi_forward(feat, rois, pool, mode="resize", out=None, argmax_out=None):
     """K-d forward.  feat (B,H,W,C) f32 channels-last, rois (B,N,4) i16/i32/f32 ->
-    out (B,N,P,P,C) f32 [, argmax (B,N,P,P,C) i32 in max mode].  custom_layers.py:35-56."""
+    out (B,N,P,P,C) f32 [, argmax (B,N,P,P,C) i32 in max mode].  custom_layers.py:35-56.
+    `out` / `argmax_out`: caller-owned result buffers (e.g. slices of a batch buffer)."""
     feat = _chk(feat, torch.float32, "feat", 4)
     if rois.dtype not in _ROI_DTYPES:
         raise TypeError("rois must be int16, int32 or float32")
@@ -188,7 +189,14 @@ def roi_forward(feat, rois, pool, mode="resize", out=None):
             raise ValueError("out buffer has the wrong shape")
     else:
         out = ctx.empty((b, n, p, p, c), torch.float32)
-    argmax = ctx.empty((b, n, p, p, c), torch.int32) if mode == "max" else None
+    argmax = None
+    if mode == "max":
+        if argmax_out is not None:
+            argmax = _chk_out(argmax_out, torch.int32, "argmax_out", 5)
+            if argmax.shape != (b, n, p, p, c):
+                raise ValueError("argmax_out buffer has the wrong shape")
+        else:
+            argmax = ctx.empty((b, n, p, p, c), torch.int32)
     ctx.call("frcnn_roi_fwd", _MODES[mode], ptr(feat), h, w, c, ptr(rois), _ROI_DTYPES[rois.dtype], n, p, b,
              ptr(out), ptr(argmax))
     return (out, argmax) if mode == "max" else out

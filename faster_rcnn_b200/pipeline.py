@@ -60,8 +60,8 @@ class ProposalRoiPipeline:
 
     def __call__(self, cls, regr, feat, on_device=None):
         """Host (or device) arrays in; returns (rois, scores, count) as numpy on the host -- what
-        `get_det_inputs` hands back in the reference -- plus the pooled features as a CUDA tensor,
-        which stay on the device for the detector head exactly like the RoI layer's output inside the
+        `get_det_inputs` hands back in the reference -- plus the pooled features as a CUDA tensor
+        ((pooled, argmax) in max mode), which stay on the device for the detector head exactly like the RoI layer's output inside the
         reference's TF graph.  `on_device(rois, scores, count)` (optional) is invoked with the device
         tensors before the read-back, e.g. to enqueue the multi-GPU all-gather of the final RoIs.
 
@@ -78,7 +78,9 @@ class ProposalRoiPipeline:
         h_rois, h_scores, h_count = (self._stage_out("rois", rois), self._stage_out("scores", scores),
                                      self._stage_out("count", count))
         torch.cuda.current_stream(self.ctx.device).synchronize()
-        return h_rois.numpy(), h_scores.numpy(), h_count.numpy(), pooled
+        # fresh arrays like the reference's get_det_inputs (det_util.py:158): the pinned staging buffers are reused by
+        # the next call and must not alias what the caller keeps (a few KB per image)
+        return h_rois.numpy().copy(), h_scores.numpy().copy(), h_count.numpy().copy(), pooled
 
     def _pinned(self, name, x):
         t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
@@ -110,8 +112,7 @@ class ProposalRoiPipeline:
         padded = self._device_buffer("o_padded", (b, m, 4), torch.int16)
         rows = self._device_buffer("o_rows", (b,), torch.int32)
         pooled = torch.empty((b, m, self.pool_size, self.pool_size, feat.shape[3]), dtype=torch.float32, device=dev)
-        if self.mode != "resize":
-            raise NotImplementedError("host-staged calls support mode='resize'; use run_device for max mode")
+        argmax = torch.empty(pooled.shape, dtype=torch.int32, device=dev) if self.mode == "max" else None
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream(dev)
@@ -131,8 +132,9 @@ class ProposalRoiPipeline:
             ops.proposals(bufs["regr"][lo:hi], bufs["cls"][lo:hi], self.anchor_dims, self.stride, self.k, self.thresh,
                           self.max_boxes, out=(rois[lo:hi], scores[lo:hi], count[lo:hi]))
             ops.pad_rois(rois[lo:hi], count[lo:hi], self.num_rois, out=(padded[lo:hi], rows[lo:hi]))
-            ops.roi_forward(bufs["feat"][lo:hi], padded[lo:hi], self.pool_size, self.mode, out=pooled[lo:hi])
-        return rois, scores, count, padded, pooled
+            ops.roi_forward(bufs["feat"][lo:hi], padded[lo:hi], self.pool_size, self.mode, out=pooled[lo:hi],
+                            argmax_out=None if argmax is None else argmax[lo:hi])
+        return rois, scores, count, padded, (pooled if argmax is None else (pooled, argmax))
 
     @staticmethod
     def h2d_bytes(cls, regr, feat):

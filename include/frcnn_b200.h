@@ -97,7 +97,12 @@ FRCNN_API int frcnn_decode_topk(frcnn_handle* h, void* stream, const float* regr
  *   predicate = f64(inter/union) <= thresh keeps, +1 areas, stop at max_boxes.
  *   keep_index [batch,max_boxes] i32 positions into the image's rows (pick
  *   order, -1 padded), keep_count [batch]; keep_boxes [batch,max_boxes,4] i16
- *   and keep_scores [batch,max_boxes] f32 are optional (NULL to skip). */
+ *   and keep_scores [batch,max_boxes] f32 are optional (NULL to skip).
+ *   Capacity: n <= FRCNN_NMS_MAX_UNSORTED for arbitrary scores; up to
+ *   FRCNN_NMS_MAX_SORTED only when an image's scores arrive STRICTLY descending
+ *   (the output of frcnn_decode_topk; equal neighbours count as unsorted).  An
+ *   image that violates this gets keep_count = -1 and an all -1 keep_index
+ *   (device-side flag, the call itself still returns FRCNN_OK). */
 FRCNN_API int frcnn_nms_i16(frcnn_handle* h, void* stream, const int16_t* boxes, const float* scores,
                   const int32_t* n, int n_max, int batch, double thresh, int max_boxes,
                   int32_t* keep_index, int32_t* keep_count, int16_t* keep_boxes,

@@ -37,6 +37,25 @@ def test_invalid_arguments_raise_with_message():
     assert int(kc[0]) >= 1
 
 
+def test_nms_i16_oversized_unsorted_input_fails_safe():
+    """More than FRCNN_NMS_MAX_UNSORTED candidates with tied scores (ties are 'not strictly descending'): the kernel
+    must not sort past its shared-memory buffer; the image is flagged with keep_count = -1 and the other image of the
+    same launch (strictly descending scores, same size) is processed normally."""
+    from faster_rcnn_b200 import ops
+    from oracle import frcnn_oracle as O
+    n = 20000
+    rng = np.random.default_rng(0)
+    x1, y1 = rng.integers(0, 50, (2, n)), rng.integers(0, 30, (2, n))
+    boxes = np.stack([x1, y1, x1 + rng.integers(1, 12, (2, n)), y1 + rng.integers(1, 12, (2, n))], axis=2).astype(np.int16)
+    scores = np.stack([np.full(n, 0.5, np.float32), np.linspace(1.0, 0.01, n, dtype=np.float32)])
+    assert np.all(np.diff(scores[1]) < 0)
+    ki, kc, kb, ks = ops.nms_i16(dev(boxes), dev(scores), None, 0.7, 300)
+    kc, ki = kc.cpu().numpy(), ki.cpu().numpy()
+    assert kc[0] == -1 and np.all(ki[0] == -1)
+    pick = O.greedy_nms(boxes[1], scores[1], 0.7, 300)
+    assert kc[1] == len(pick) and np.array_equal(ki[1, :kc[1]], pick)
+
+
 def test_python_layer_type_checks():
     import torch
     from faster_rcnn_b200 import det_util, ops

@@ -307,11 +307,21 @@ def test_pipeline_host_staged_equals_device_path(ops):
     d_rois, d_scores, d_count, d_padded, d_pooled = pipe.run_device(dev(cls), dev(regr), dev(feat))
     assert np.array_equal(rois, host(d_rois)) and np.array_equal(scores, host(d_scores)) and np.array_equal(count, host(d_count))
     assert torch.equal(pooled, d_pooled)
-    again = pipe(cls, regr, feat)                      # buffers are reused across calls
-    assert np.array_equal(again[0], rois) and torch.equal(again[3], d_pooled)
+    keep = rois.copy()
+    again = pipe(cls[::-1].copy(), regr[::-1].copy(), feat[::-1].copy())     # staging buffers are reused across calls ...
+    assert not np.shares_memory(again[0], rois) and np.array_equal(rois, keep)   # ... but results are the caller's own arrays
+    assert np.array_equal(again[0], rois[::-1]) and torch.equal(again[3], d_pooled.flip(0))
     from oracle import roi_oracle as R
     n0 = int(count[0])
     assert np.array_equal(host(pooled)[0, :n0], R.roi_resize_fwd(feat[0], rois[0, :n0], 7))
+    # max mode through the same host-staged call (the north-star's pooling variant)
+    mpipe = ProposalRoiPipeline(dims, 16, 2000, 0.7, 300, 64, 7, "max", h2d_chunk=2)
+    m_rois, _, m_count, (m_pooled, m_arg) = mpipe(cls, regr, feat)
+    assert np.array_equal(m_rois, rois) and np.array_equal(m_count, count)
+    dm_pooled, dm_arg = mpipe.run_device(dev(cls), dev(regr), dev(feat))[4]
+    assert torch.equal(m_pooled, dm_pooled) and torch.equal(m_arg, dm_arg)
+    wout, warg = R.roi_max_fwd(feat[0], rois[0, :n0], 7)
+    assert np.array_equal(host(m_pooled)[0, :n0], wout) and np.array_equal(host(m_arg)[0, :n0], warg)
 
 
 def test_pipeline_cuda_graph_replay_equals_eager(ops):
