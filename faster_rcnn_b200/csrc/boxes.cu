@@ -52,8 +52,8 @@ box_transform_kernel(float4* __restrict__ boxes, const float4* __restrict__ delt
     y = __fadd_rn(y, __fdiv_rn(h, 2.0f));
     x = __fadd_rn(x, __fmul_rn(t.x, w));
     y = __fadd_rn(y, __fmul_rn(t.y, h));
-    w = __fmul_rn(w, expf(t.z));
-    h = __fmul_rn(h, expf(t.w));
+    w = __fmul_rn(w, np_expf(t.z));
+    h = __fmul_rn(h, np_expf(t.w));
     x = __fsub_rn(x, __fdiv_rn(w, 2.0f));
     y = __fsub_rn(y, __fdiv_rn(h, 2.0f));
     x = rintf(x); y = rintf(y); w = rintf(w); h = rintf(h);

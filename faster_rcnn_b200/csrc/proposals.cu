@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ r
     y = __fadd_rn(y, __fdiv_rn(hgt, 2.0f));
     x = __fadd_rn(x, __fmul_rn(tx, w));
     y = __fadd_rn(y, __fmul_rn(ty, hgt));
-    w = __fmul_rn(w, expf(tw));
-    hgt = __fmul_rn(hgt, expf(th));
+    w = __fmul_rn(w, np_expf(tw));
+    hgt = __fmul_rn(hgt, np_expf(th));
     x = __fsub_rn(x, __fdiv_rn(w, 2.0f));
     y = __fsub_rn(y, __fdiv_rn(hgt, 2.0f));
     x = rintf(x); y = rintf(y); w = rintf(w); hgt = rintf(hgt);     // np.round: half to even

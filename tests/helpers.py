@@ -42,6 +42,32 @@ class FakeRpn:
         return [self.cls, self.regr] + ([self.conv] if self.conv is not None else [])
 
 
+def np_exp_f32_simd(x):
+    """numpy's own float32 `exp` kernel (numpy >= 1.17 on x86 with AVX2 / AVX512F: simd_exp_FLOAT in
+    loops_exponent_log.dispatch.c.src), restated with FMAs emulated in float64.  The device's np_expf() (common.cuh)
+    is this sequence; numpy_exp_is_simd_kernel() tells whether the numpy of this machine dispatches to it."""
+    f = np.float32
+    x = np.asarray(x, f)
+
+    def fma(a, b, c):
+        return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(f)
+    q = (x * f(1.44269504088896340736)).astype(f)
+    q = ((q + f(12582912.0)).astype(f) - f(12582912.0)).astype(f)
+    r = fma(q, f(-6.93145752e-1), x)
+    r = fma(q, f(-1.42860677e-6), r)
+    num = fma(f(5.082762527590693718096e-04), r, f(6.757896990527504603057e-03))
+    for c in (5.114512081637298353406e-02, 2.473615434895520810817e-01, 7.257664613233124478488e-01, 9.999999999980870924916e-01):
+        num = fma(num, r, f(c))
+    den = fma(fma(f(2.159509375685829852307e-02), r, f(-2.742335390411667452936e-01)), r, f(1.0))
+    return np.ldexp((num / den).astype(f), q.astype(np.int32)).astype(f)
+
+
+def numpy_exp_is_simd_kernel():
+    """True when np.exp on a STRIDED float32 column (what util.py:131 passes) equals np_exp_f32_simd bit for bit."""
+    x = (np.random.default_rng(7).standard_normal((200000, 4)) * 0.6).astype(np.float32)
+    return bool(np.array_equal(np.exp(x[:, 2]), np_exp_f32_simd(x[:, 2])))
+
+
 def flipped_rows(got, want):
     """rows where two integer-valued box arrays differ (decode flips caused by expf ulps)."""
     return np.where(np.any(got != want, axis=1))[0]

@@ -100,3 +100,17 @@ def test_labels_on_real_voc_ground_truth():
         cu, ip, _ = O.label_anchors(w, h, gt, rows, cols, dims, 16)
         assert hashlib.sha1(cu.tobytes() + ip.tobytes()).hexdigest()[:16] == str(g["label_sha1"][i])
         assert int(ip.sum()) == int(g["n_pos"][i]) and int(cu.sum()) == int(g["n_use"][i])
+
+
+def test_numpy_float32_exp_kernel_restatement():
+    """np_expf (csrc/common.cuh) restates numpy's SIMD float32 exp; its Python twin in tests/helpers.py must reproduce
+    np.exp bit for bit wherever numpy dispatches to that kernel (this container: AVX512F), incl. the range ends."""
+    from helpers import np_exp_f32_simd, numpy_exp_is_simd_kernel
+    if not numpy_exp_is_simd_kernel():
+        pytest.skip("this machine's numpy does not use its SIMD float32 exp kernel")
+    rng = np.random.default_rng(11)
+    x = np.concatenate([(rng.standard_normal(2_000_000) * s).astype(np.float32) for s in (0.05, 0.5, 3.0, 20.0)])
+    assert np.array_equal(np.exp(x), np_exp_f32_simd(x))
+    # not the correctly rounded exp: the reason a double-precision exp on the device would NOT reproduce the reference
+    exact = np.exp(x.astype(np.float64)).astype(np.float32)
+    assert 0.2 < np.mean(np.exp(x) != exact) < 0.6
