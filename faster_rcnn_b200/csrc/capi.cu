@@ -88,6 +88,26 @@ int arena_get(frcnn_handle* h, cudaStream_t stream, size_t bytes, void** out) {
   return FRCNN_OK;
 }
 
+// The scratch arena is per handle and is reused by every call.  Calls on ONE stream are ordered by the stream.  When a
+// call arrives on a different stream than the previous call, the new stream first waits (on the device) for
+// everything already enqueued on the previous stream, so kernels of the two calls can never share scratch
+// concurrently.  A stream that is being captured is left alone (cross-stream dependencies would leak into the
+// capture): captured sequences run on a private handle (pipeline.GraphedRun).
+int stream_handover(frcnn_handle* h, cudaStream_t st) {
+  if (h->last_stream_set && h->last_stream != st) {
+    cudaStreamCaptureStatus a = cudaStreamCaptureStatusNone, b = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &a);
+    cudaStreamIsCapturing(h->last_stream, &b);
+    if (a == cudaStreamCaptureStatusNone && b == cudaStreamCaptureStatusNone) {
+      FRCNN_CUDA(h, cudaEventRecord(h->handover, h->last_stream));
+      FRCNN_CUDA(h, cudaStreamWaitEvent(st, h->handover, 0));
+    }
+  }
+  h->last_stream = st;
+  h->last_stream_set = 1;
+  return FRCNN_OK;
+}
+
 static int make_table(frcnn_handle* h, const int32_t* anchor_hw_host, int n_anchors, int divide_by, AnchorTable* tab) {
   if (!anchor_hw_host || n_anchors <= 0 || n_anchors > FRCNN_MAX_ANCHORS)
     return fail(h, FRCNN_ERR_INVALID, "anchor table: need 1..FRCNN_MAX_ANCHORS [height,width] rows%s%s");
@@ -114,7 +134,9 @@ using namespace frcnn;
   {                                                                          \
     cudaError_t e_ = cudaSetDevice((h)->device);                             \
     if (e_ != cudaSuccess) return frcnn::fail((h), FRCNN_ERR_CUDA, "cudaSetDevice: %s%s", cudaGetErrorString(e_)); \
-    int rc_ = frcnn::arena_reset((h), st);                                   \
+    int rc_ = frcnn::stream_handover((h), st);                               \
+    if (rc_) return rc_;                                                     \
+    rc_ = frcnn::arena_reset((h), st);                                       \
     if (rc_) return rc_;                                                     \
   }
 
@@ -140,6 +162,10 @@ int frcnn_create(frcnn_handle** out, int device) {
     delete h;
     return FRCNN_ERR_UNSUPPORTED;
   }
+  if (cudaEventCreateWithFlags(&h->handover, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return FRCNN_ERR_CUDA;
+  }
   *out = h;
   return FRCNN_OK;
 }
@@ -149,6 +175,7 @@ void frcnn_destroy(frcnn_handle* h) {
   cudaSetDevice(h->device);
   for (int i = 0; i < h->n_overflow; ++i) cudaFree(h->overflow[i]);
   if (h->arena) cudaFree(h->arena);
+  if (h->handover) cudaEventDestroy(h->handover);
   delete h;
 }
 

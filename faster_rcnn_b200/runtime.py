@@ -13,6 +13,8 @@ from . import _lib
 
 _contexts = {}
 _lock = threading.Lock()
+_tls = threading.local()          # per-thread context overrides (use_context)
+_PIN_RING = 4                     # pinned staging buffers per (dtype, size): reuse waits on that buffer's own copy only
 
 
 class Context:
@@ -77,17 +79,28 @@ class Context:
         a = np.ascontiguousarray(array, dtype=dtype)
         t = torch.from_numpy(a)
         key = ("h2d", t.dtype, t.numel())
-        pin = self._pinned.get(key)
-        if pin is None:
-            pin = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+        ring = self._pinned.get(key)
+        if ring is None:
             if len(self._pinned) > 64:
                 self._pinned.clear()
-            self._pinned[key] = pin
+            ring = self._pinned[key] = {"next": 0, "slots": []}
+        if len(ring["slots"]) < _PIN_RING:
+            ring["slots"].append([torch.empty(t.numel(), dtype=t.dtype).pin_memory(), None])
+            slot = ring["slots"][-1]
         else:
-            # the previous async copy out of this buffer must have drained before it is rewritten
-            torch.cuda.current_stream(self.device).synchronize()
+            slot = ring["slots"][ring["next"]]
+            ring["next"] = (ring["next"] + 1) % _PIN_RING
+            # only THIS buffer's previous upload (whatever stream issued it) must have drained before it is rewritten;
+            # with a ring of buffers that copy is several uploads old, so the wait is normally already satisfied
+            if slot[1] is not None:
+                slot[1].synchronize()
+        pin = slot[0]
         pin.copy_(t.reshape(-1))
-        return pin.to(self.device, non_blocking=True).reshape(t.shape)
+        out = pin.to(self.device, non_blocking=True).reshape(t.shape)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(self.device))
+        return out
 
     def to_host(self, tensor):
         """device tensor -> numpy (synchronous)."""
@@ -99,6 +112,9 @@ def get_context(device=None):
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     if isinstance(device, torch.device):
         device = device.index if device.index is not None else torch.cuda.current_device()
+    override = getattr(_tls, "override", None)
+    if override and device in override:
+        return override[device]
     with _lock:
         ctx = _contexts.get(device)
         if ctx is None:
@@ -108,24 +124,25 @@ def get_context(device=None):
 
 
 class use_context:
-    """`with use_context(ctx):` makes `get_context(ctx.device)` return `ctx` inside the block.  Used to run (and
-    capture) a sequence of ops on a PRIVATE handle whose scratch arena nobody else can grow or move afterwards."""
+    """`with use_context(ctx):` makes `get_context(ctx.device)` return `ctx` inside the block, FOR THE CALLING THREAD
+    only (other threads keep the shared per-device context).  Used to run (and capture) a sequence of ops on a PRIVATE
+    handle whose scratch arena nobody else can grow or move afterwards."""
 
     def __init__(self, ctx):
         self.ctx, self.prev = ctx, None
 
     def __enter__(self):
-        with _lock:
-            self.prev = _contexts.get(self.ctx.device.index)
-            _contexts[self.ctx.device.index] = self.ctx
+        if not hasattr(_tls, "override"):
+            _tls.override = {}
+        self.prev = _tls.override.get(self.ctx.device.index)
+        _tls.override[self.ctx.device.index] = self.ctx
         return self.ctx
 
     def __exit__(self, *exc):
-        with _lock:
-            if self.prev is None:
-                _contexts.pop(self.ctx.device.index, None)
-            else:
-                _contexts[self.ctx.device.index] = self.prev
+        if self.prev is None:
+            _tls.override.pop(self.ctx.device.index, None)
+        else:
+            _tls.override[self.ctx.device.index] = self.prev
         return False
 
 

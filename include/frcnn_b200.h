@@ -19,12 +19,23 @@
  *  - one handle per (host thread, device); handles are not thread-safe.  A
  *    handle owns a scratch arena that grows on demand (growing synchronises the
  *    stream; call frcnn_reserve() up front to avoid that, e.g. before CUDA-graph
- *    capture).
+ *    capture).  The arena is shared by all calls on the handle: calls on one
+ *    stream are ordered by the stream; a call on a DIFFERENT stream than the
+ *    previous call first makes its stream wait (device-side event) for the work
+ *    the handle enqueued on the previous stream, so two streams never use the
+ *    scratch concurrently -- use one handle per stream for real concurrency.  A
+ *    stream under CUDA-graph capture is exempt: capture on a private handle.
+ *  - deviation from SURVEY.md 8b: there is no frcnn_workspace_bytes() and no
+ *    `*_host` convenience variant.  Scratch is the handle's arena (pre-sized with
+ *    frcnn_reserve), and the host<->device copies of the drop-in layer are done
+ *    by the Python binding through pinned staging buffers (runtime.py).
  *  - boxes are [x1, y1, x2, y2]; a "batch" is a set of independent images laid
  *    out contiguously (image-major).  Flat anchor index = (y*C + x)*A + a.
  *  - arithmetic follows the reference bit for bit where it is integer / IEEE
  *    (+1 area convention and f64 ratio in NMS, f32 no-FMA IoU in labelling);
- *    see DESIGN.md for the two documented transcendental exceptions (expf/log).
+ *    the decode evaluates numpy's own float32 exp kernel (np_expf); float64
+ *    log/exp in regression targets and post-processing follow the device libm
+ *    (<= 1 ulp after the float32 store).
  */
 #ifndef FRCNN_B200_H
 #define FRCNN_B200_H

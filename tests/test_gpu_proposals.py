@@ -386,3 +386,26 @@ def test_fused_proposals_with_tied_scores(ops, levels, k, max_boxes):
     rois, sc, cnt = ops.proposals(dev(regr), dev(cls), dims, 16, k, 0.7, max_boxes)
     m = int(host(cnt)[0])
     assert m == len(pick) and np.array_equal(host(rois)[0, :m], wb[pick]) and np.array_equal(host(sc)[0, :m], wp[pick])
+
+
+def test_one_handle_two_streams_share_scratch_safely(ops):
+    """The per-handle scratch arena is reused by every call; a call on another stream must first wait for the previous
+    stream's work (capi.cu stream_handover).  Back-to-back fused proposal calls on two streams without any host
+    synchronisation give the single-stream results."""
+    import torch
+    dims = O.anchor_table([128, 256, 512])
+    a = _synth(38, 63, [128, 256, 512], 71, True)
+    b = _synth(38, 63, [128, 256, 512], 72, True)
+    big = [torch.cat([dev(x[i])] * 32) for x in (a, b) for i in (1, 2)]       # cls_a, regr_a, cls_b, regr_b, 32 images each
+    want_a = [t.clone() for t in ops.proposals(big[1], big[0], dims, 16, 12000, 0.7, 2000)]
+    want_b = [t.clone() for t in ops.proposals(big[3], big[2], dims, 16, 12000, 0.7, 2000)]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            got_a = ops.proposals(big[1], big[0], dims, 16, 12000, 0.7, 2000)
+        with torch.cuda.stream(s2):
+            got_b = ops.proposals(big[3], big[2], dims, 16, 12000, 0.7, 2000)
+        torch.cuda.synchronize()
+        for w, g in zip(want_a + want_b, list(got_a) + list(got_b)):
+            assert torch.equal(w, g)
