@@ -201,6 +201,46 @@ __device__ void radix_select2(const unsigned long long* __restrict__ keys, const
   __syncthreads();
 }
 
+// Suffix scan over a TOPK_BINS histogram: the bin that holds the need-th largest element (1-based).
+// out[0] = bin, out[1] = rank of that element inside the bin, out[2] = size of the bin.  Block-wide; ends with a barrier.
+__device__ __forceinline__ void find_bucket(const unsigned* hh, int need, int* warp_tot, int* out) {
+  const int tid = threadIdx.x;
+  const int c0 = (int)hh[TOPK_BINS - 1 - 2 * tid], c1 = (int)hh[TOPK_BINS - 2 - 2 * tid];
+  const int incl = block_inclusive_scan(c0 + c1, warp_tot);
+  const int excl = incl - c0 - c1;
+  if (excl < need && excl + c0 >= need) { out[0] = TOPK_BINS - 1 - 2 * tid; out[1] = need - excl; out[2] = c0; }
+  else if (excl + c0 < need && incl >= need) { out[0] = TOPK_BINS - 2 - 2 * tid; out[1] = need - excl - c0; out[2] = c1; }
+  __syncthreads();
+}
+
+// Exact selection inside ONE top-digit bucket whose keys sit in shared memory (`st`, n_st keys, all with the same top
+// TOPK_BITS bits = prefix >> 53): the key T with exactly `need` bucket keys >= T.  11-bit passes over the stash only --
+// no global sweep; one or two passes for float scores.
+__device__ unsigned long long select_in_stash(const unsigned long long* st, int n_st, unsigned long long prefix, int need,
+                                              unsigned* hist, int* warp_tot, int* s_out) {
+  int hi = 64 - TOPK_BITS;
+  while (true) {
+    const int bits = hi < TOPK_BITS ? hi : TOPK_BITS, shift = hi - bits;
+    for (int i = threadIdx.x; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_st; i += TOPK_THREADS) {
+      const unsigned long long key = st[i];
+      if ((key >> hi) == (prefix >> hi)) atomicAdd(&hist[(unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u))], 1u);
+    }
+    __syncthreads();
+    find_bucket(hist, need, warp_tot, s_out);
+    const int d = s_out[0], rest = s_out[1], cnt = s_out[2];
+    prefix |= (unsigned long long)d << shift;
+    need = rest;
+    hi = shift;
+    if (shift == 0 || cnt == rest) break;            // bucket taken whole: the low bits are free
+  }
+  __syncthreads();
+  return prefix;
+}
+
+constexpr int TOPK_STASH = 6144;                     // boundary-bucket keys a CTA can resolve in shared memory (48 KB)
+
 // `splits` CTAs per image.  CTA r produces ranks [r*k/splits, (r+1)*k/splits) of the descending top-k
 // order on its own: it selects the two splitters that bound its slice (exact radix select over all
 // keys of the image, L2-resident), compacts the keys between them into shared memory and sorts them
@@ -218,7 +258,7 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
   __shared__ unsigned hist[2 * TOPK_BINS];
   __shared__ int warp_tot[TOPK_WARPS];
   __shared__ unsigned long long s_prefix[2];
-  __shared__ int s_need[2], s_done[2], s_count;
+  __shared__ int s_need[2], s_done[2], s_count, s_sel[4], s_stash[2];
 
   const int img = blockIdx.x / splits, part = blockIdx.x - img * splits;
   const unsigned long long* keys = keys_all + (size_t)img * n;
@@ -233,9 +273,69 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
   const int slice_end = (int)((long long)(part + 1) * k / splits);
   const int last = min(slice_end, m);
 
-  // splitters: keys >= t_lo and < t_hi are exactly the ranks [first, last)
   unsigned long long t_hi = ~0ull, t_lo = 1ull;
-  if (first < last) {
+  // Slice membership.  decode_kernel histogrammed the keys' top 11 bits; the buckets of the two slice bounds follow from
+  // that histogram alone.  ONE sweep over the image's keys then sends every key strictly between the two boundary
+  // buckets straight into the slice and parks the keys OF the boundary buckets in a shared-memory stash; the exact
+  // splitters are resolved inside the stash (select_in_stash) and the stash keys on the right side of them join the slice.
+  // The first version swept the keys three times (two select passes + compaction), each sweep an L2 round trip chain;
+  // it remains as the fall-back when the boundary buckets outgrow the stash (scores crowded into one quarter-octave).
+  unsigned long long* stash = sbuf + (M + TOPK_THREADS);
+  bool done = first >= last;
+  if (!done) {
+    const bool need_hi = first > 0, need_lo = last < n_valid;
+    for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = (unsigned)__ldg(meta + 1 + i);
+    __syncthreads();
+    int da = TOPK_BINS, rest_a = 0, cnt_a = 0, db = -1, rest_b = 0, cnt_b = 0;
+    if (need_hi) {
+      find_bucket(hist, first, warp_tot, s_sel);
+      da = s_sel[0]; rest_a = s_sel[1]; cnt_a = s_sel[2];
+      __syncthreads();
+    }
+    if (need_lo) {
+      find_bucket(hist, last, warp_tot, s_sel);
+      db = s_sel[0]; rest_b = s_sel[1]; cnt_b = s_sel[2];
+      __syncthreads();
+    }
+    const bool one_bucket = da == db;
+    const int n_stash_a = cnt_a, n_stash_b = one_bucket ? 0 : cnt_b;
+    if (n_stash_a + n_stash_b <= TOPK_STASH) {
+      done = true;
+      if (tid == 0) { s_stash[0] = 0; s_stash[1] = 0; }
+      __syncthreads();
+      for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
+        unsigned long long kk[TOPK_U];
+#pragma unroll
+        for (int u = 0; u < TOPK_U; ++u) {
+          const int i = base + u * TOPK_THREADS + tid;
+          kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < TOPK_U; ++u) {
+          const int dg = (int)(kk[u] >> (64 - TOPK_BITS));
+          const bool valid = kk[u] != 0ull;
+          const bool take = valid && dg < da && dg > db;
+          const unsigned ballot = __ballot_sync(0xffffffffu, take);
+          int wbase = 0;
+          if (lane == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          if (take) sbuf[pad_slot<E>(wbase + __popc(ballot & ((1u << lane) - 1u)))] = kk[u];
+          if (valid && dg == da) stash[atomicAdd(&s_stash[0], 1)] = kk[u];
+          else if (valid && dg == db) stash[n_stash_a + atomicAdd(&s_stash[1], 1)] = kk[u];
+        }
+      }
+      __syncthreads();
+      if (need_hi) t_hi = select_in_stash(stash, n_stash_a, (unsigned long long)da << (64 - TOPK_BITS), rest_a, hist, warp_tot, s_sel);
+      if (need_lo) t_lo = one_bucket ? select_in_stash(stash, n_stash_a, (unsigned long long)db << (64 - TOPK_BITS), rest_b, hist, warp_tot, s_sel)
+                                     : select_in_stash(stash + n_stash_a, n_stash_b, (unsigned long long)db << (64 - TOPK_BITS), rest_b, hist, warp_tot, s_sel);
+      for (int i = tid; i < n_stash_a + n_stash_b; i += TOPK_THREADS) {
+        const unsigned long long key = stash[i];
+        if (key >= t_lo && (first == 0 || key < t_hi)) sbuf[pad_slot<E>(atomicAdd(&s_count, 1))] = key;
+      }
+    }
+  }
+  if (!done) {
+    // fall-back: exact splitters by radix select over all keys (keys >= t_lo and < t_hi are exactly the ranks [first, last))
     const bool need_hi = first > 0, need_lo = last < n_valid;
     unsigned long long ta = 0ull, tb = 0ull;
     if (need_hi && need_lo) {
@@ -249,10 +349,7 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
       radix_select2(keys, meta + 1, n, last, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
       t_lo = ta;
     }
-  }
-
-  // compaction of the slice into shared memory (order irrelevant, sorted next)
-  if (first < last) {
+    // compaction of the slice into shared memory (order irrelevant, sorted next)
     for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
       unsigned long long kk[TOPK_U];
 #pragma unroll
@@ -351,7 +448,7 @@ template <int E>
 static int launch_topk(frcnn_handle* h, cudaStream_t stream, const unsigned long long* keys, const BoxI16* boxes,
                        const float* cls, const int* valid_count, int n, int k, int splits, int batch, BoxI16* out_boxes,
                        float* out_scores, int32_t* out_index, int32_t* out_count) {
-  const size_t smem = (size_t)(TOPK_THREADS * E + TOPK_THREADS) * sizeof(unsigned long long);
+  const size_t smem = (size_t)(TOPK_THREADS * E + TOPK_THREADS + TOPK_STASH) * sizeof(unsigned long long);
   if (smem + 12 * 1024 > (size_t)h->max_smem_optin)
     return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k too large for the shared-memory sort%s%s");
   FRCNN_CUDA(h, cudaFuncSetAttribute(topk_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
