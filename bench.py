@@ -347,6 +347,11 @@ def measure_stages(ops, dev, rank, world, peak, want_dump):
             nbytes[k + "_fwd"] = nbytes[k + "_bwd"] = io + pooled * (2 if mode == "max" else 1)
             del arg
         del feat, gout
+    # input pipeline on the device: 16 decoded 375x500 BGR images -> bicubic 600x800 + mirror + mean subtraction
+    raw = torch.randint(0, 256, (16, 375, 500, 3), dtype=torch.uint8, device=dev)
+    ms["f4_image_resize_preprocess_b16"] = timeit(lambda: ops.image_resize_cubic(raw, 600, 800, flip=True, mean=ops.IMAGENET_MEAN_BGR))
+    nbytes["f4_image_resize_preprocess_b16"] = 16 * (375 * 500 * 3 + 600 * 800 * 3 * (1 + 4))
+    del raw
     if want_dump:
         pairs = [synth.rpn_outputs(ROWS, COLS, len(voc), 1000 + i) for i in range(2)]
         regr1, cls1 = np.concatenate([p[1] for p in pairs]), np.concatenate([p[0] for p in pairs])

@@ -45,6 +45,11 @@ int launch_voc_match(frcnn_handle*, cudaStream_t, const double*, const int32_t*,
 int launch_voc_pr_ap(frcnn_handle*, cudaStream_t, const double*, const double*, int, double, const double*, int, double*,
                      double*, double*);
 
+int launch_image_resize(frcnn_handle*, cudaStream_t, const uint8_t*, int, int, int, int, int, int, int, const double*,
+                        uint8_t*, float*);
+int launch_gt_transform(frcnn_handle*, cudaStream_t, const double*, const int32_t*, int, int, const double*, const double*,
+                        double*);
+
 // ---- scratch arena -------------------------------------------------------------------------
 // Bump allocator over one device block.  Every public entry point starts with arena_reset();
 // the launchers then carve their workspaces with arena_get().  When a call needs more than the
@@ -451,6 +456,28 @@ int frcnn_voc_pr_ap(frcnn_handle* h, void* stream, const double* tp, const doubl
   FRCNN_REQUIRE(h, ap && thresholds && n_thresholds > 0, "voc_pr_ap: null pointer");
   FRCNN_REQUIRE(h, n_dets >= 0 && (n_dets == 0 || (tp && fp && rec && prec)), "voc_pr_ap: null pointer");
   return launch_voc_pr_ap(h, st, tp, fp, n_dets, npos, thresholds, n_thresholds, rec, prec, ap);
+}
+
+int frcnn_image_resize_cubic(frcnn_handle* h, void* stream, const uint8_t* src, int src_height, int src_width,
+                             int channels, int dst_height, int dst_width, int flip, int batch,
+                             const double* mean_host, uint8_t* out_u8, float* out_f32) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, src && (out_u8 || out_f32), "image_resize_cubic: null pointer");
+  FRCNN_REQUIRE(h, src_height > 0 && src_width > 0 && dst_height > 0 && dst_width > 0 && batch > 0 && batch <= 65535,
+                "image_resize_cubic: bad size");
+  FRCNN_REQUIRE(h, channels >= 1 && channels <= 4, "image_resize_cubic: 1..4 channels");
+  FRCNN_REQUIRE(h, (long long)src_height * src_width * channels < (1LL << 31) && (dst_height + 7) / 8 <= 65535,
+                "image_resize_cubic: image too large");
+  return launch_image_resize(h, st, src, src_height, src_width, channels, dst_height, dst_width, flip, batch, mean_host,
+                             out_u8, out_f32);
+}
+
+int frcnn_gt_transform(frcnn_handle* h, void* stream, const double* boxes, const int32_t* n_box, int n_max, int batch,
+                       const double* ratio, const double* flip_width, double* out) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, boxes && ratio && out, "gt_transform: null pointer");
+  FRCNN_REQUIRE(h, n_max > 0 && batch > 0 && batch <= 65535, "gt_transform: bad size");
+  return launch_gt_transform(h, st, boxes, n_box, n_max, batch, ratio, flip_width, out);
 }
 
 }  // extern "C"

@@ -7,6 +7,7 @@ images.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -376,3 +377,45 @@ def voc_pr_ap(tp, fp, npos, thresholds):
     ctx.call("frcnn_voc_pr_ap", ptr(tp), ptr(fp), nd, float(npos), ptr(thresholds), thresholds.numel(), ptr(rec), ptr(prec),
              ptr(ap))
     return rec, prec, ap
+
+
+# ---- host-side input pipeline on the device -------------------------------------------------------------
+IMAGENET_MEAN_BGR = (103.939, 116.779, 123.68)     # keras.applications.imagenet_utils.preprocess_input ('caffe' mode)
+
+
+def image_resize_cubic(images, dst_height, dst_width, flip=False, mean=None, want_u8=True):
+    """shapes.py:19-29 on the device: images (B,H,W,C) u8 (BGR, as cv2.imread) -> cv2.resize(INTER_CUBIC) [+ cv2.flip(.., 1)].
+    Returns u8 (B,dst_h,dst_w,C) when `want_u8`, and additionally float32 pixels minus `mean` (C floats, the subtraction
+    of resnet.preprocess, resnet.py:64-75) when `mean` is given: u8, (u8, f32) or f32."""
+    images = _chk(images, torch.uint8, "images", 4)
+    ctx = get_context(images.device)
+    b, h, w, c = images.shape
+    if not want_u8 and mean is None:
+        raise ValueError("nothing to compute: want_u8=False and no mean")
+    out_u8 = ctx.empty((b, int(dst_height), int(dst_width), c), torch.uint8) if want_u8 else None
+    out_f = ctx.empty((b, int(dst_height), int(dst_width), c), torch.float32) if mean is not None else None
+    mean_arr = None
+    if mean is not None:
+        mean_arr = np.ascontiguousarray(np.asarray(mean, dtype=np.float64).reshape(-1))
+        if mean_arr.shape[0] != c:
+            raise ValueError("mean must have one entry per channel")
+    ctx.call("frcnn_image_resize_cubic", ptr(images), h, w, c, int(dst_height), int(dst_width), int(bool(flip)), b,
+             None if mean_arr is None else mean_arr.ctypes.data_as(C.c_void_p), ptr(out_u8), ptr(out_f))
+    if out_u8 is not None and out_f is not None:
+        return out_u8, out_f
+    return out_u8 if out_u8 is not None else out_f
+
+
+def gt_transform(boxes, ratio, flip_width=None, n_box=None):
+    """shapes.py:93-101 / 292-300 on the device: boxes (B,G,4) f64 corners * ratio (B,) f64, then mirrored about
+    flip_width (B,) f64 where it is >= 0 -> (B,G,4) f64 (rows >= n_box zeroed)."""
+    boxes, ratio = _chk(boxes, torch.float64, "boxes", 3), _chk(ratio, torch.float64, "ratio", 1)
+    if flip_width is not None:
+        flip_width = _chk(flip_width, torch.float64, "flip_width", 1)
+    if n_box is not None:
+        n_box = _chk(n_box, torch.int32, "n_box", 1)
+    ctx = get_context(boxes.device)
+    b, g, _ = boxes.shape
+    out = ctx.empty((b, g, 4), torch.float64)
+    ctx.call("frcnn_gt_transform", ptr(boxes), ptr(n_box), g, b, ptr(ratio), ptr(flip_width), ptr(out))
+    return out

@@ -1,11 +1,12 @@
-"""Minimal host-side value objects accepted by the drop-in managers.
+"""Host-side value objects accepted by the drop-in managers (reference: shapes.py).
 
 The managers only read ``.width .height .gt_boxes[*].corners/.obj_cls/.resize()
 .cache_key .data`` (reference: shapes.py:5-132,187-305), so any duck-typed
-object works, including the reference's own ``shapes.Image``.  These light
-classes exist so tests, the bench and users without the reference checkout can
-build inputs; there is no image decoding here (pixels are out of scope for the
-proposal / target path).
+object works, including the reference's own ``shapes.Image``.  ``Image`` can be
+built from in-memory pixels or from an ``image_path`` (lazy ``cv2.imread`` like
+the reference); ``.data`` is the reference's host path (cv2 resize + flip),
+``.data_device()`` / ``.preprocessed_device()`` do the resize, flip and mean
+subtraction on the GPU (`ops.image_resize_cubic`).
 """
 import numpy as np
 
@@ -96,25 +97,63 @@ class GroundTruthBox:
 
 
 class Image:
-    """Image metadata + optional in-memory pixels (reference: shapes.py:5-132)."""
+    """Image metadata + pixels (reference: shapes.py:5-132).  Pixels come from `data` (an in-memory BGR uint8 array of
+    ANY size: it is resized to width x height on access, like the reference resizes what it reads from disk) or, lazily,
+    from `image_path`."""
 
-    def __init__(self, name, width, height, gt_boxes=(), flipped=False, data=None):
+    def __init__(self, name, width, height, gt_boxes=(), flipped=False, data=None, image_path=None):
         self.name, self.width, self.height = name, width, height
-        self.gt_boxes, self.flipped, self._data = list(gt_boxes), flipped, data
+        self.gt_boxes, self.flipped, self._data, self.image_path = list(gt_boxes), flipped, data, image_path
 
     @property
     def cache_key(self):
         return self.name + str(self.flipped)
 
+    def _raw(self):
+        if self._data is not None:
+            return self._data
+        if self.image_path is None:
+            raise ValueError("image %s carries no pixels" % self.name)
+        import cv2
+        img = cv2.imread(self.image_path)
+        if img is None:
+            raise IOError("cannot read %s" % self.image_path)
+        return img
+
     @property
     def data(self):
-        if self._data is None:
-            raise ValueError("image %s carries no pixels" % self.name)
-        return self._data
+        """shapes.py:19-29 on the host: the pixels resized (INTER_CUBIC) to width x height and mirrored when flipped.
+        In-memory pixels that already have that size are returned as they are (they were resized by the caller)."""
+        img = self._raw()
+        if self.image_path is None and (img.ndim < 2 or img.shape[:2] == (self.height, self.width) or img.dtype != np.uint8):
+            return img                                  # synthetic / already prepared arrays (tests, bench)
+        import cv2
+        img = cv2.resize(img, (self.width, self.height), interpolation=cv2.INTER_CUBIC)
+        return cv2.flip(img, 1) if self.flipped and self.image_path is not None else img
+
+    def data_device(self, mean=None, want_u8=True):
+        """The same pixels computed on the GPU from the raw decoded image (one H2D of the uint8 pixels): returns the
+        (height,width,C) u8 CUDA tensor, or with `mean` the float32 mean-subtracted tensor as well (ops.image_resize_cubic).
+        Within one grey level of `.data` (OpenCV's own SIMD / generic code paths differ by as much, oracle/image_oracle.py)."""
+        from . import ops
+        from .runtime import get_context
+        raw = np.ascontiguousarray(self._raw())
+        if raw.dtype != np.uint8 or raw.ndim != 3:
+            raise TypeError("data_device needs (H,W,C) uint8 pixels")
+        dev = get_context().to_device(raw[None])
+        out = ops.image_resize_cubic(dev, self.height, self.width, flip=self.flipped and self.image_path is not None,
+                                     mean=mean, want_u8=want_u8)
+        return tuple(t[0] for t in out) if isinstance(out, tuple) else out[0]
+
+    def preprocessed_device(self, mean=None):
+        """float32 (1,height,width,C) CUDA tensor = resized (+ mirrored) BGR pixels minus the ImageNet means: what
+        `batched_image` feeds the backbone (det_util.py:36, resnet.py:64-75), without leaving the device."""
+        from . import ops
+        return self.data_device(mean=ops.IMAGENET_MEAN_BGR if mean is None else mean, want_u8=False)[None]
 
     def resize(self, ratio):
         w, h = int(round(ratio * self.width)), int(round(ratio * self.height))
-        return Image(self.name, w, h, [g.resize(ratio) for g in self.gt_boxes], self.flipped, self._data)
+        return Image(self.name, w, h, [g.resize(ratio) for g in self.gt_boxes], self.flipped, self._data, self.image_path)
 
     def resize_within_bounds(self, min_size, max_size):
         short, long_ = min(self.width, self.height), max(self.width, self.height)
@@ -124,10 +163,13 @@ class Image:
 
     def horizontal_flip(self):
         """mirrored copy: boxes flipped about the image width, `flipped` toggled, so `cache_key` differs
-        (reference: shapes.py:126-132,227-234); pixels are mirrored by the caller's loader, not here."""
-        flipped = None if self._data is None else self._data[:, ::-1]
+        (reference: shapes.py:126-132,227-234).  In-memory pixels are mirrored here; pixels read from `image_path` are
+        mirrored on access, like the reference does."""
+        flipped = None if self._data is None or self.image_path is not None else self._data[:, ::-1]
+        if self.image_path is not None:
+            flipped = self._data
         return Image(self.name, self.width, self.height, [g.horizontal_flip(self.width) for g in self.gt_boxes],
-                     not self.flipped, flipped)
+                     not self.flipped, flipped, self.image_path)
 
     @property
     def num_gt_boxes(self):

@@ -292,6 +292,24 @@ FRCNN_API int frcnn_voc_pr_ap(frcnn_handle* h, void* stream, const double* tp, c
                               double npos, const double* thresholds, int n_thresholds, double* rec,
                               double* prec, double* ap);
 
+/* ---- host-side input pipeline on the device
+ * Pixels of shapes.Image.data (shapes.py:19-29: cv2.resize(INTER_CUBIC) then cv2.flip(img, 1) when `flip`) for a
+ * batch of equally sized uint8 images [batch,H,W,channels] (BGR as cv2.imread returns them).  OpenCV's generic
+ * fixed-point bicubic (A = -0.75, x2048 short coefficients, (sum + 2^21) >> 22): within one grey level of cv2.resize.
+ *   out_u8 [batch,dst_h,dst_w,channels] and / or out_f32 (same shape, float32 = pixel - mean_host[c], the mean
+ *   subtraction of resnet.preprocess / vgg.preprocess, resnet.py:64-75; mean_host = `channels` doubles on the HOST,
+ *   NULL = zeros) -- either may be NULL. */
+FRCNN_API int frcnn_image_resize_cubic(frcnn_handle* h, void* stream, const uint8_t* src, int src_height, int src_width,
+                             int channels, int dst_height, int dst_width, int flip, int batch,
+                             const double* mean_host, uint8_t* out_u8, float* out_f32);
+
+/* GT boxes of a resized / mirrored image (shapes.py:93-101 Box.resize, :292-300 horizontal_flip): boxes
+ * [batch,n_max,4] f64 corners, n_box [batch] i32 (NULL = n_max), ratio [batch] f64, flip_width [batch] f64 (NULL or a
+ * negative entry = not mirrored; else the width the box is mirrored about) -> out [batch,n_max,4] f64; float64 like
+ * the reference's Python floats, rows >= n_box zeroed. */
+FRCNN_API int frcnn_gt_transform(frcnn_handle* h, void* stream, const double* boxes, const int32_t* n_box, int n_max,
+                       int batch, const double* ratio, const double* flip_width, double* out);
+
 #ifdef __cplusplus
 }
 #endif
