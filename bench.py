@@ -346,6 +346,13 @@ def measure_stages(ops, dev, rank, world, peak, want_dump):
             ms[k + "_bwd"] = timeit(lambda: ops.roi_backward(gout, rois5, (b5, ROWS, COLS, CHANNELS), mode, arg))
             nbytes[k + "_fwd"] = nbytes[k + "_bwd"] = io + pooled * (2 if mode == "max" else 1)
             del arg
+        # max mode with the one-byte arg-max (5 instead of 8 bytes per pooled element)
+        code = ops.roi_forward(feat, rois5, POOL, "max", compact=True)[1]
+        k = "c5_roi_max_u8arg_b%d" % b5
+        ms[k + "_fwd"] = timeit(lambda: ops.roi_forward(feat, rois5, POOL, "max", compact=True))
+        ms[k + "_bwd"] = timeit(lambda: ops.roi_backward(gout, rois5, (b5, ROWS, COLS, CHANNELS), "max", code))
+        nbytes[k + "_fwd"] = nbytes[k + "_bwd"] = io + pooled + pooled // 4
+        del code
         del feat, gout
     # input pipeline on the device: 16 decoded 375x500 BGR images -> bicubic 600x800 + mirror + mean subtraction
     raw = torch.randint(0, 256, (16, 375, 500, 3), dtype=torch.uint8, device=dev)
@@ -531,7 +538,7 @@ def run_ours(args, rank, world, local_rank):
             stages[k] = row
         stages["_sizes"] = dict(st_sizes, c5="1 and 8 images x 2000 RoIs per GPU and launch, 38x63x1024 f32 features",
                                 note="per-GPU work (weak scaling); ms = max over ranks; frac = algorithmic bytes / ms / measured "
-                                     "HBM copy peak for the HBM-bound stages; max-mode bytes count the int32 arg-max")
+                                     "HBM copy peak for the HBM-bound stages; max-mode bytes count the int32 arg-max, the max_u8arg rows the one-byte one")
         stages["c5_img_per_s_fwd_bwd_resize"] = round(world * 1e3 / (st_ms["c5_roi_resize_b1_fwd"] + st_ms["c5_roi_resize_b1_bwd"]), 1)
         stages["c5_img_per_s_fwd_bwd_max"] = round(world * 1e3 / (st_ms["c5_roi_max_b1_fwd"] + st_ms["c5_roi_max_b1_bwd"]), 1)
         line = {

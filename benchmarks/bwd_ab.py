@@ -50,6 +50,26 @@ def main():
         rois = torch.from_numpy(np.stack([synth.random_rois(n_rois, h, w, 7 + i) for i in range(batch)])).cuda()
         gout = torch.randn((batch, n_rois, p, p, c), device="cuda")
         for mode in args.modes.split(","):
+            if mode == "maxc":                                    # max mode with the one-byte arg-max, forward + backward
+                nb = 4 * batch * h * w * c + 8 * batch * n_rois + 5 * batch * n_rois * p * p * c
+                code = ops.roi_forward(feat, rois, p, "max", compact=True)[1]
+                want = ops.roi_backward(gout, rois, (batch, h, w, c), "max", ops.roi_forward(feat, rois, p, "max")[1])
+                ms = timeit(lambda: ops.roi_forward(feat, rois, p, "max", compact=True), args.iters, 3)
+                row = {"case": tag, "mode": "maxc_fwd", "ms": round(ms, 4), "frac_5B": round(nb / ms / 1e6 / PEAK, 3)}
+                res.append(row)
+                print(json.dumps(row), flush=True)
+                for cfg in ({}, {"FRCNN_BWD_CPB": 2, "FRCNN_BWD_DEPTH": 4}, {"FRCNN_BWD_CPB": 1, "FRCNN_BWD_DEPTH": 8}):
+                    setenv(cfg)
+                    got = ops.roi_backward(gout, rois, (batch, h, w, c), "max", code)
+                    err = (got - want).abs().max().item() / want.abs().max().item()
+                    ms = timeit(lambda: ops.roi_backward(gout, rois, (batch, h, w, c), "max", code), args.iters, 3)
+                    row = {"case": tag, "mode": "maxc_bwd", "cfg": cfg, "ms": round(ms, 4), "frac_5B": round(nb / ms / 1e6 / PEAK, 3),
+                           "rel_err_vs_int32": err}
+                    res.append(row)
+                    print(json.dumps(row), flush=True)
+                setenv({})
+                del code, want
+                continue
             arg = ops.roi_forward(feat, rois, p, "max")[1] if mode == "max" else None
             nbytes = 4 * batch * h * w * c + 8 * batch * n_rois + 4 * batch * n_rois * p * p * c * (2 if mode == "max" else 1)
             setenv({"FRCNN_BWD_IMPL": "cell"})

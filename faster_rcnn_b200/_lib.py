@@ -35,6 +35,9 @@ SIGNATURES = {
     "frcnn_label_rois": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "frcnn_roi_fwd": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p]),
     "frcnn_roi_bwd": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "frcnn_roi_compact_supported": (_i, [_i, _i, _i, _i]),
+    "frcnn_roi_max_fwd_compact": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p]),
+    "frcnn_roi_max_bwd_compact": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "frcnn_det_postprocess": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _i, _i, _p, _p, _p, _p]),
     "frcnn_cross_ious": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
     "frcnn_box_transform": (_i, [_p, _p, _p, _p, _i, _i, _i, _i]),

@@ -20,9 +20,10 @@ int launch_pack_rpn(frcnn_handle*, cudaStream_t, uint8_t*, const uint8_t*, const
 int launch_label_rois(frcnn_handle*, cudaStream_t, const int16_t*, const int32_t*, int, const double*,
                       const int32_t*, const int32_t*, int, int, int, int16_t*, int32_t*, float*, int32_t*, int32_t*);
 int launch_roi_fwd(frcnn_handle*, cudaStream_t, int, const float*, int, int, int, const void*, int, int, int, int,
-                   float*, int32_t*);
+                   float*, int32_t*, int);
 int launch_roi_bwd(frcnn_handle*, cudaStream_t, int, const float*, const void*, int, const int32_t*, int, int, int,
-                   int, int, int, float*);
+                   int, int, int, float*, int);
+bool roi_compact_supported(int, int, int, int);
 int launch_det_postprocess(frcnn_handle*, cudaStream_t, const int16_t*, const float*, const float*, const double*,
                            const int32_t*, int, int, int, int, double, double, int, int, int32_t*, float*, int32_t*, int32_t*);
 
@@ -321,7 +322,35 @@ int frcnn_roi_fwd(frcnn_handle* h, void* stream, int mode, const float* feat, in
                 "roi_fwd: non-positive size");
   FRCNN_REQUIRE(h, batch <= 65535, "roi_fwd: batch > 65535");
   return launch_roi_fwd(h, st, mode, feat, height, width, channels, rois, roi_dtype, n_rois, pool, batch, out,
-                        argmax);
+                        argmax, 0);
+}
+
+int frcnn_roi_compact_supported(int height, int width, int channels, int pool) {
+  return roi_compact_supported(height, width, channels, pool) && pool <= 8 ? 1 : 0;
+}
+
+int frcnn_roi_max_fwd_compact(frcnn_handle* h, void* stream, const float* feat, int height, int width, int channels,
+                              const void* rois, int roi_dtype, int n_rois, int pool, int batch, float* out,
+                              uint8_t* argmax_u8) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, feat && rois && out && argmax_u8, "roi_max_fwd_compact: null pointer");
+  FRCNN_REQUIRE(h, roi_dtype >= FRCNN_ROI_I16 && roi_dtype <= FRCNN_ROI_F32, "roi_max_fwd_compact: unknown roi dtype");
+  FRCNN_REQUIRE(h, height > 0 && width > 0 && channels > 0 && n_rois > 0 && pool > 0 && batch > 0 && batch <= 65535,
+                "roi_max_fwd_compact: bad size");
+  return launch_roi_fwd(h, st, FRCNN_ROI_MAX, feat, height, width, channels, rois, roi_dtype, n_rois, pool, batch, out,
+                        reinterpret_cast<int32_t*>(argmax_u8), 1);
+}
+
+int frcnn_roi_max_bwd_compact(frcnn_handle* h, void* stream, const float* grad_out, const void* rois, int roi_dtype,
+                              const uint8_t* argmax_u8, int height, int width, int channels, int n_rois, int pool,
+                              int batch, float* grad_feat) {
+  FRCNN_ENTER(h, stream);
+  FRCNN_REQUIRE(h, grad_out && rois && grad_feat && argmax_u8, "roi_max_bwd_compact: null pointer");
+  FRCNN_REQUIRE(h, roi_dtype >= FRCNN_ROI_I16 && roi_dtype <= FRCNN_ROI_F32, "roi_max_bwd_compact: unknown roi dtype");
+  FRCNN_REQUIRE(h, height > 0 && width > 0 && channels > 0 && n_rois > 0 && pool > 0 && batch > 0 && batch <= 65535,
+                "roi_max_bwd_compact: bad size");
+  return launch_roi_bwd(h, st, FRCNN_ROI_MAX, grad_out, rois, roi_dtype, reinterpret_cast<const int32_t*>(argmax_u8), height,
+                        width, channels, n_rois, pool, batch, grad_feat, 1);
 }
 
 int frcnn_roi_bwd(frcnn_handle* h, void* stream, int mode, const float* grad_out, const void* rois, int roi_dtype,
@@ -336,7 +365,7 @@ int frcnn_roi_bwd(frcnn_handle* h, void* stream, int mode, const float* grad_out
                 "roi_bwd: non-positive size");
   FRCNN_REQUIRE(h, batch <= 65535, "roi_bwd: batch > 65535");
   return launch_roi_bwd(h, st, mode, grad_out, rois, roi_dtype, argmax, height, width, channels, n_rois, pool,
-                        batch, grad_feat);
+                        batch, grad_feat, 0);
 }
 
 int frcnn_det_postprocess(frcnn_handle* h, void* stream, const int16_t* rois, const float* out_cls,

@@ -88,7 +88,10 @@ constexpr int ROI_FWD_THREADS = 64;
 constexpr int ROI_MAX_TABLE_P = 32;     // table-driven kernels support pool sizes up to 32
 
 // Forward: one CTA per (RoI, 256-channel block, image); a thread owns four consecutive channels.
-template <int MODE>
+// COMPACT (max mode only): the arg-max is stored as ONE BYTE per element, (dy << 4) | dx relative to the bin's first
+// cell, instead of the int32 flat cell index: 5 instead of 8 bytes per pooled element leave the kernel (and enter the
+// backward).  Bins are at most ceil(H/P)+1 cells high / wide; the launcher takes this path only when that is <= 16.
+template <int MODE, bool COMPACT = false>
 __global__ void __launch_bounds__(ROI_FWD_THREADS)
 roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* __restrict__ rois, int dtype,
                int N, int P, int ph_groups, float* __restrict__ out, int* __restrict__ argmax) {
@@ -120,7 +123,8 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
   if (s_crop.z <= 0 || s_crop.w <= 0) {   // TF would raise on an empty crop; we emit zeros
     for (int b = ph0 * P; b < ph1 * P; ++b) {
       st_cs_f4(out + obase + (size_t)b * C, make_float4(0.f, 0.f, 0.f, 0.f));
-      if (MODE == FRCNN_ROI_MAX) st_cs_i4(argmax + obase + (size_t)b * C, make_int4(0, 0, 0, 0));
+      if (MODE == FRCNN_ROI_MAX && !COMPACT) st_cs_i4(argmax + obase + (size_t)b * C, make_int4(0, 0, 0, 0));
+      if (MODE == FRCNN_ROI_MAX && COMPACT) __stcs(reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(argmax) + obase + (size_t)b * C), 0u);
     }
     return;
   }
@@ -211,15 +215,19 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
       int yb = s_tap[ph].x >> 16;
       float* o = out + obase + (size_t)(ph0 * P + pw) * C;
       int* oa = argmax + obase + (size_t)(ph0 * P + pw) * C;
+      unsigned char* oc = reinterpret_cast<unsigned char*>(argmax) + obase + (size_t)(ph0 * P + pw) * C;   // COMPACT
       float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
       int4 arg = make_int4(0, 0, 0, 0);
       bool open = false;
+      int ya_open = y_begin;                          // first row of the open bin (COMPACT: dy is relative to it)
       for (int y = y_begin; ph < ph1; ++y, rowp += row_bytes, cell0 += W) {
         float4 rb;
         int4 ra;
+        if (!open) ya_open = y;
+        const int code0 = COMPACT ? ((y - ya_open) << 4) : cell0;      // arg value of the segment's first cell
 #define FRCNN_ROW_STEP(J)                                                                    \
   {                                                                                          \
-    const int cj_ = cell0 + (J);                                                             \
+    const int cj_ = code0 + (J);                                                             \
     if (v_[J].x > rb.x) { rb.x = v_[J].x; ra.x = cj_; }                                      \
     if (v_[J].y > rb.y) { rb.y = v_[J].y; ra.y = cj_; }                                      \
     if (v_[J].z > rb.z) { rb.z = v_[J].z; ra.z = cj_; }                                      \
@@ -231,7 +239,7 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
     _Pragma("unroll") for (int j = 0; j < BW; ++j)                                           \
       v_[j] = ldg_f4(reinterpret_cast<const float*>(rowp + j * cell_bytes));                 \
     rb = v_[0];                                                                              \
-    ra = make_int4(cell0, cell0, cell0, cell0);                                              \
+    ra = make_int4(code0, code0, code0, code0);                                              \
     _Pragma("unroll") for (int j = 1; j < BW; ++j) FRCNN_ROW_STEP(j)                         \
   }
         if (bw == 2) FRCNN_ROW_SCAN(2)
@@ -242,7 +250,7 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
           FRCNN_ROW_SCAN(4)
           for (int x = 4; x < bw; ++x) {
             const float4 v1 = ldg_f4(reinterpret_cast<const float*>(rowp + x * cell_bytes));
-            const int cj_ = cell0 + x;
+            const int cj_ = code0 + x;
             if (v1.x > rb.x) { rb.x = v1.x; ra.x = cj_; }
             if (v1.y > rb.y) { rb.y = v1.y; ra.y = cj_; }
             if (v1.z > rb.z) { rb.z = v1.z; ra.z = cj_; }
@@ -263,15 +271,21 @@ roi_fwd_kernel(const float* __restrict__ feat, int H, int W, int C, const void* 
         }
         while (y == yb - 1) {                         // the open bin ends on this row
           st_cs_f4(o, best);
-          st_cs_i4(oa, arg);
+          if (COMPACT) {
+            __stcs(reinterpret_cast<unsigned*>(oc), (unsigned)arg.x | ((unsigned)arg.y << 8) | ((unsigned)arg.z << 16) | ((unsigned)arg.w << 24));
+          } else {
+            st_cs_i4(oa, arg);
+          }
           o += (size_t)P * C;
           oa += (size_t)P * C;
+          oc += (size_t)P * C;
           if (++ph == ph1) break;
           const int t = s_tap[ph].x;
           yb = t >> 16;
           if ((t & 0xffff) <= y) {                    // the next bin starts on (or repeats) this row
             best = rb;
-            arg = ra;
+            arg = COMPACT ? make_int4(ra.x & 15, ra.y & 15, ra.z & 15, ra.w & 15) : ra;      // dy = 0 in the new bin
+            ya_open = y;
           } else {
             open = false;
             break;
@@ -694,12 +708,19 @@ static int build_tables(frcnn_handle* h, cudaStream_t stream, int mode, const vo
   return FRCNN_OK;
 }
 
+// true when the one-byte arg-max format can describe every bin of an H x W map pooled to P x P
+bool roi_compact_supported(int H, int W, int C, int P) {
+  return C % 4 == 0 && P >= 1 && P <= ROI_MAX_TABLE_P && (H + P - 1) / P + 1 <= 16 && (W + P - 1) / P + 1 <= 16;
+}
+
 int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* feat, int H, int W, int C,
-                   const void* rois, int dtype, int N, int P, int batch, float* out, int32_t* argmax) {
+                   const void* rois, int dtype, int N, int P, int batch, float* out, int32_t* argmax, int compact) {
+  if (compact && (mode != FRCNN_ROI_MAX || !roi_compact_supported(H, W, C, P) || (reinterpret_cast<uintptr_t>(argmax) & 3)))
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "roi_fwd: compact arg-max needs max mode, C %% 4 == 0 and bins of at most 16 x 16 cells%s%s");
   if (C % 4 == 0 && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768 && (long long)W * C < (1LL << 29) &&
       (reinterpret_cast<uintptr_t>(feat) % 16 == 0) &&
       (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
-      (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0)) {
+      (mode != FRCNN_ROI_MAX || compact || reinterpret_cast<uintptr_t>(argmax) % 16 == 0)) {
     const int cblocks = (C / 4 + ROI_FWD_THREADS - 1) / ROI_FWD_THREADS;
     // max mode, fewer than 8 waves of CTAs (20 resident per SM): split every RoI into two row groups (same-box A/B at
     // 2000 RoIs x 1 image: 0.252 ms with one group, 0.236 with two or three, 0.265 with P groups -- more groups break
@@ -709,9 +730,12 @@ int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
     dim3 grid(N, cblocks * ph_groups, batch);
     if (mode == FRCNN_ROI_RESIZE)
       roi_fwd_kernel<FRCNN_ROI_RESIZE><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, ph_groups, out, argmax);
+    else if (compact)
+      roi_fwd_kernel<FRCNN_ROI_MAX, true><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, ph_groups, out, argmax);
     else
       roi_fwd_kernel<FRCNN_ROI_MAX><<<grid, ROI_FWD_THREADS, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, ph_groups, out, argmax);
   } else {
+    if (compact) return fail(h, FRCNN_ERR_UNSUPPORTED, "roi_fwd: compact arg-max needs 16-byte aligned buffers%s%s");
     dim3 grid(N, (C + 127) / 128, batch);
     if (mode == FRCNN_ROI_RESIZE)
       roi_fwd_scalar_kernel<FRCNN_ROI_RESIZE><<<grid, 128, 0, stream>>>(feat, H, W, C, rois, dtype, N, P, out, argmax);
@@ -724,16 +748,23 @@ int launch_roi_fwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* 
 
 bool roi_bwd_blk_eligible(int mode, int H, int W, int C, int N, int P);
 int launch_roi_bwd_blk(frcnn_handle*, cudaStream_t, int, const float*, const void*, int, const int32_t*, int, int, int,
-                       int, int, int, float*);
+                       int, int, int, float*, int);
 
 int launch_roi_bwd(frcnn_handle* h, cudaStream_t stream, int mode, const float* gout, const void* rois, int dtype,
-                   const int32_t* argmax, int H, int W, int C, int N, int P, int batch, float* gfeat) {
+                   const int32_t* argmax, int H, int W, int C, int N, int P, int batch, float* gfeat, int compact) {
+  if (compact) {
+    const bool ok = mode == FRCNN_ROI_MAX && roi_compact_supported(H, W, C, P) && roi_bwd_blk_eligible(mode, H, W, C, N, P) &&
+                    (reinterpret_cast<uintptr_t>(gout) % 16 == 0) && (reinterpret_cast<uintptr_t>(gfeat) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(argmax) % 4 == 0);
+    if (!ok) return fail(h, FRCNN_ERR_UNSUPPORTED, "roi_bwd: compact arg-max needs max mode, C %% 4 == 0, pool <= 8 and bins of at most 16 x 16 cells%s%s");
+    return launch_roi_bwd_blk(h, stream, mode, gout, rois, dtype, argmax, H, W, C, N, P, batch, gfeat, 1);
+  }
   const bool aligned = (reinterpret_cast<uintptr_t>(gout) % 16 == 0) && (reinterpret_cast<uintptr_t>(gfeat) % 16 == 0) &&
                        (mode != FRCNN_ROI_MAX || reinterpret_cast<uintptr_t>(argmax) % 16 == 0);
   {
     const char* impl = getenv("FRCNN_BWD_IMPL");          // "cell": force the round-1 cell-stationary kernels (A/B runs)
     if (aligned && roi_bwd_blk_eligible(mode, H, W, C, N, P) && !(impl && impl[0] == 'c'))
-      return launch_roi_bwd_blk(h, stream, mode, gout, rois, dtype, argmax, H, W, C, N, P, batch, gfeat);
+      return launch_roi_bwd_blk(h, stream, mode, gout, rois, dtype, argmax, H, W, C, N, P, batch, gfeat, 0);
   }
   if (C % 4 == 0 && aligned && P <= ROI_MAX_TABLE_P && H < 32768 && W < 32768) {
     int4 *crops = nullptr, *taps = nullptr;

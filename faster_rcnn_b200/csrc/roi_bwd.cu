@@ -29,6 +29,7 @@ namespace frcnn {
 constexpr int BLK = 2;                       // block edge in cells
 constexpr unsigned ENT_MASK_SHIFT = 28;      // entry word = dY row index | cell mask << 28
 constexpr unsigned ENT_IDX_MASK = (1u << ENT_MASK_SHIFT) - 1u;
+constexpr int ROI_MAX_COMPACT = 2;           // internal mode: max pooling with the one-byte (dy << 4 | dx) arg-max of roi.cu
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -37,6 +38,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async16_if(void* smem_dst, const void* gsrc, bool pred) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }"
+               ::"r"(s), "l"(gsrc), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async4_if(void* smem_dst, const void* gsrc, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 4; }"
                ::"r"(s), "l"(gsrc), "r"((int)pred) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
@@ -209,7 +215,20 @@ roi_bwd_plan_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, 
       const int ph = __ffs(my) - 1, pw = __ffs(mx) - 1;
       const unsigned row = (unsigned)((r * P + ph) * P + pw);
       const unsigned pos = pos_warp + (unsigned)e;
-      if (MODE == FRCNN_ROI_RESIZE) {
+      if (MODE == ROI_MAX_COMPACT) {
+        // the block's four cells as arg-max codes of THIS bin ((dy << 4) | dx from the bin's first cell); a cell the
+        // code cannot describe (outside [0,16) in either direction) gets 0xffff, which no stored byte equals
+        const Crop c = load_crop(rois, dtype, (size_t)img * N + r, W, H);
+        const int ya = c.y1 + (ph * c.h) / P, xa = c.x1 + (pw * c.w) / P;
+        unsigned code[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int dy = Y0 + (q >> 1) - ya, dx = X0 + (q & 1) - xa;
+          code[q] = ((unsigned)dy < 16u && (unsigned)dx < 16u) ? (unsigned)((dy << 4) | dx) : 0xffffu;
+        }
+        ent_idx[pos] = row;
+        reinterpret_cast<uint4*>(ent_w)[pos] = make_uint4(code[0], code[1], code[2], code[3]);
+      } else if (MODE == FRCNN_ROI_RESIZE) {
         const Crop c = load_crop(rois, dtype, (size_t)img * N + r, W, H);
         float wy0, wy1, wx0, wx1;
         const unsigned hy = axis_weights(ph, (float)c.h / (float)P, c.h, c.y1 - Y0, wy0, wy1);
@@ -233,9 +252,10 @@ constexpr int BLK_WARPS = 8;
 
 template <int MODE, int CPB, int D>
 struct BlkSmem {
-  static constexpr int ROW_F4 = (MODE == FRCNN_ROI_MAX ? 2 : 1) * CPB * 32;   // one ring slot: dY row (+ arg-max row)
+  // one ring slot: dY row (+ arg-max row: int32 = as large again, one byte per element = a quarter)
+  static constexpr int ROW_F4 = CPB * 32 + (MODE == FRCNN_ROI_MAX ? CPB * 32 : (MODE == ROI_MAX_COMPACT ? CPB * 8 : 0));
   static constexpr int RING_F4 = D * ROW_F4;
-  static constexpr int ENT_F4 = (MODE == FRCNN_ROI_RESIZE ? 64 : 0) + 16;     // 2 x 32 weights + 2 x 32 index words
+  static constexpr int ENT_F4 = (MODE != FRCNN_ROI_MAX ? 64 : 0) + 16;        // 2 x 32 weights / cell codes + 2 x 32 index words
   static constexpr int WARP_F4 = RING_F4 + ENT_F4;
   static constexpr size_t BYTES = (size_t)BLK_WARPS * WARP_F4 * 16;
 };
@@ -252,8 +272,8 @@ roi_bwd_blk_kernel(const float* __restrict__ gout, const int* __restrict__ argma
   extern __shared__ float4 smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* ring = smem + warp * S::WARP_F4;
-  float4* entw = ring + S::RING_F4;                                           // resize mode only
-  unsigned* enti = reinterpret_cast<unsigned*>(ring + S::RING_F4 + (MODE == FRCNN_ROI_RESIZE ? 64 : 0));
+  float4* entw = ring + S::RING_F4;                                           // resize: tap weights; compact max: cell codes
+  unsigned* enti = reinterpret_cast<unsigned*>(ring + S::RING_F4 + (MODE != FRCNN_ROI_MAX ? 64 : 0));
   const int unit = blockIdx.x * UNITS + warp / PARTS, part = warp % PARTS;
   const int img = blockIdx.z;
   const bool live = unit < n_blocks;
@@ -272,8 +292,9 @@ roi_bwd_blk_kernel(const float* __restrict__ gout, const int* __restrict__ argma
   const size_t img_off = (size_t)img * N * P * P * C;
   const float* g_img = gout + img_off;
   const int* a_img = (MODE == FRCNN_ROI_MAX) ? argmax + img_off : nullptr;
+  const unsigned char* a8_img = (MODE == ROI_MAX_COMPACT) ? reinterpret_cast<const unsigned char*>(argmax) + img_off : nullptr;
   const unsigned* ei = ent_idx + begin;
-  const float4* ew = (MODE == FRCNN_ROI_RESIZE) ? ent_w + begin : nullptr;
+  const float4* ew = (MODE != FRCNN_ROI_MAX) ? ent_w + begin : nullptr;
 
   float4 acc[4][CPB];
 #pragma unroll
@@ -290,7 +311,7 @@ roi_bwd_blk_kernel(const float* __restrict__ gout, const int* __restrict__ argma
   auto fetch_batch = [&](int b) {
     const int e = 32 * b + lane;
     if (e < n) {
-      if (MODE == FRCNN_ROI_RESIZE) cp_async16(entw + (b & 1) * 32 + lane, ew + e);
+      if (MODE != FRCNN_ROI_MAX) cp_async16(entw + (b & 1) * 32 + lane, ew + e);
       cp_async4(enti + (b & 1) * 32 + lane, ei + e);
     }
   };
@@ -305,6 +326,8 @@ roi_bwd_blk_kernel(const float* __restrict__ gout, const int* __restrict__ argma
     for (int j = 0; j < CPB; ++j) {
       cp_async16_if(slot + j * 32, g_img + off + coff[j], p);
       if (MODE == FRCNN_ROI_MAX) cp_async16_if(slot + (CPB + j) * 32, a_img + off + coff[j], p);
+      if (MODE == ROI_MAX_COMPACT)
+        cp_async4_if(reinterpret_cast<unsigned*>(ring + s * S::ROW_F4 + CPB * 32) + j * 32 + lane, a8_img + off + coff[j], p);
     }
   };
   // add list entry i (its rows sit in ring slot `s`) into the four cells
@@ -334,6 +357,22 @@ roi_bwd_blk_kernel(const float* __restrict__ gout, const int* __restrict__ argma
       FRCNN_BLK_ACCUM(2, w.z)
       FRCNN_BLK_ACCUM(3, w.w)
 #undef FRCNN_BLK_ACCUM
+    } else if (MODE == ROI_MAX_COMPACT) {
+      const uint4 code = *reinterpret_cast<const uint4*>(entw + (i & 63));
+      const unsigned cq[4] = {code.x, code.y, code.z, code.w};
+#pragma unroll
+      for (int j = 0; j < CPB; ++j) {
+        const float4 g = slot[j * 32];
+        const unsigned a = (reinterpret_cast<const unsigned*>(ring + s * S::ROW_F4 + CPB * 32) + j * 32)[lane];
+        const unsigned ax = a & 0xffu, ay = (a >> 8) & 0xffu, az = (a >> 16) & 0xffu, aw = a >> 24;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (ax == cq[q]) acc[q][j].x += g.x;
+          if (ay == cq[q]) acc[q][j].y += g.y;
+          if (az == cq[q]) acc[q][j].z += g.z;
+          if (aw == cq[q]) acc[q][j].w += g.w;
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < CPB; ++j) {
@@ -467,7 +506,7 @@ bool roi_bwd_blk_eligible(int mode, int H, int W, int C, int N, int P) {
 }
 
 int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const float* gout, const void* rois, int dtype,
-                       const int32_t* argmax, int H, int W, int C, int N, int P, int batch, float* gfeat) {
+                       const int32_t* argmax, int H, int W, int C, int N, int P, int batch, float* gfeat, int compact) {
   const int blocks_x = (W + BLK - 1) / BLK, blocks_y = (H + BLK - 1) / BLK, n_blocks = blocks_x * blocks_y;
   // upper bound of the list entries: a resize bin has taps in <= 2 x 2 blocks; a max bin spans <= ceil(H/P)+1 rows
   long long per_bin = 4;
@@ -485,7 +524,7 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   if ((rc = arena_get(h, stream, (size_t)batch * blocks_y * n_pad, &p_ym))) return rc;
   if ((rc = arena_get(h, stream, (size_t)batch * blocks_x * n_pad, &p_xm))) return rc;
   if ((rc = arena_get(h, stream, (size_t)cap * sizeof(unsigned), &p_idx))) return rc;
-  if (mode == FRCNN_ROI_RESIZE && (rc = arena_get(h, stream, (size_t)cap * sizeof(float4), &p_w))) return rc;
+  if ((mode == FRCNN_ROI_RESIZE || compact) && (rc = arena_get(h, stream, (size_t)cap * sizeof(float4), &p_w))) return rc;
   FRCNN_CUDA(h, cudaMemsetAsync(p_cnt, 0, 4, stream));
   dim3 mgrid((n_pad + 255) / 256, blocks_y + blocks_x, batch), pgrid(n_blocks, batch);
   uint8_t *ym = static_cast<uint8_t*>(p_ym), *xm = static_cast<uint8_t*>(p_xm);
@@ -497,6 +536,9 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   if (mode == FRCNN_ROI_RESIZE) {
     roi_bwd_mask_kernel<FRCNN_ROI_RESIZE><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
     if (N > 1024) FRCNN_PLAN(FRCNN_ROI_RESIZE, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_RESIZE, 4); else FRCNN_PLAN(FRCNN_ROI_RESIZE, 2);
+  } else if (compact) {
+    roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
+    if (N > 1024) FRCNN_PLAN(ROI_MAX_COMPACT, 8); else if (N > 256) FRCNN_PLAN(ROI_MAX_COMPACT, 4); else FRCNN_PLAN(ROI_MAX_COMPACT, 2);
   } else {
     roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
     if (N > 1024) FRCNN_PLAN(FRCNN_ROI_MAX, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_MAX, 4); else FRCNN_PLAN(FRCNN_ROI_MAX, 2);
@@ -510,6 +552,11 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   if (mode == FRCNN_ROI_RESIZE) {
     if (!((cpb == 2 && (depth == 8 || depth == 4)) || (cpb == 1 && (depth == 16 || depth == 8 || depth == 4)))) {
       cpb = C >= 256 ? 2 : 1;
+      depth = 8;
+    }
+  } else if (compact) {
+    if (!((cpb == 2 && (depth == 4 || depth == 8)) || (cpb == 1 && depth == 8))) {
+      cpb = 1;
       depth = 8;
     }
   } else if (!((cpb == 2 && depth == 4) || (cpb == 1 && (depth == 8 || depth == 4)))) {
@@ -543,6 +590,11 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
     if (cpb == 1 && depth == 16) { FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 1, 16) }
     if (cpb == 1 && depth == 4) { FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 1, 4) }
     FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 1, 8)
+  }
+  if (compact) {
+    if (cpb == 2 && depth == 4) { FRCNN_BLK_GO(ROI_MAX_COMPACT, 2, 4) }
+    if (cpb == 2 && depth == 8) { FRCNN_BLK_GO(ROI_MAX_COMPACT, 2, 8) }
+    FRCNN_BLK_GO(ROI_MAX_COMPACT, 1, 8)
   }
   if (cpb == 2 && depth == 4) { FRCNN_BLK_GO(FRCNN_ROI_MAX, 2, 4) }
   if (cpb == 1 && depth == 4) { FRCNN_BLK_GO(FRCNN_ROI_MAX, 1, 4) }

@@ -23,7 +23,9 @@ class _RoiFunction(torch.autograd.Function):
     def forward(ctx, feat, rois, pool, mode):
         feat = feat.contiguous()
         if mode == "max":
-            out, argmax = ops.roi_forward(feat, rois, pool, "max")
+            # the arg-max only feeds the backward: take the one-byte format whenever the bins allow it
+            compact = rois.shape[1] < 65536 and ops.roi_compact_supported(feat.shape[1], feat.shape[2], feat.shape[3], pool)
+            out, argmax = ops.roi_forward(feat, rois, pool, "max", compact=compact)
         else:
             out, argmax = ops.roi_forward(feat, rois, pool, "resize"), None
         ctx.mode, ctx.feat_shape = mode, tuple(feat.shape)

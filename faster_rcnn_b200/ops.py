@@ -173,10 +173,16 @@ def label_rois(rois, gt, gt_cls, n_gt, n_classes, n_roi=None):
     return out_rois, out_cls, out_bbreg, src, count
 
 
-def roi_forward(feat, rois, pool, mode="resize", out=None, argmax_out=None):
+def roi_compact_supported(height, width, channels, pool):
+    """True when max mode can use the one-byte arg-max (every bin fits 16 x 16 cells, C % 4 == 0, pool <= 8)."""
+    return bool(_lib.load().frcnn_roi_compact_supported(int(height), int(width), int(channels), int(pool)))
+
+
+def roi_forward(feat, rois, pool, mode="resize", out=None, argmax_out=None, compact=False):
     """K-d forward.  feat (B,H,W,C) f32 channels-last, rois (B,N,4) i16/i32/f32 ->
-    out (B,N,P,P,C) f32 [, argmax (B,N,P,P,C) i32 in max mode].  custom_layers.py:35-56.
-    `out` / `argmax_out`: caller-owned result buffers (e.g. slices of a batch buffer)."""
+    out (B,N,P,P,C) f32 [, argmax (B,N,P,P,C) in max mode: i32 flat cell index y*W+x, or with `compact=True` u8
+    (dy << 4) | dx relative to the bin's first cell (training fast path, see include/frcnn_b200.h)].
+    custom_layers.py:35-56.  `out` / `argmax_out`: caller-owned result buffers (e.g. slices of a batch buffer)."""
     feat = _chk(feat, torch.float32, "feat", 4)
     if rois.dtype not in _ROI_DTYPES:
         raise TypeError("rois must be int16, int32 or float32")
@@ -191,28 +197,41 @@ def roi_forward(feat, rois, pool, mode="resize", out=None, argmax_out=None):
     else:
         out = ctx.empty((b, n, p, p, c), torch.float32)
     argmax = None
+    if compact and mode != "max":
+        raise ValueError("compact arg-max exists in max mode only")
     if mode == "max":
+        adt = torch.uint8 if compact else torch.int32
         if argmax_out is not None:
-            argmax = _chk_out(argmax_out, torch.int32, "argmax_out", 5)
+            argmax = _chk_out(argmax_out, adt, "argmax_out", 5)
             if argmax.shape != (b, n, p, p, c):
                 raise ValueError("argmax_out buffer has the wrong shape")
         else:
-            argmax = ctx.empty((b, n, p, p, c), torch.int32)
+            argmax = ctx.empty((b, n, p, p, c), adt)
+    if compact:
+        ctx.call("frcnn_roi_max_fwd_compact", ptr(feat), h, w, c, ptr(rois), _ROI_DTYPES[rois.dtype], n, p, b, ptr(out),
+                 ptr(argmax))
+        return out, argmax
     ctx.call("frcnn_roi_fwd", _MODES[mode], ptr(feat), h, w, c, ptr(rois), _ROI_DTYPES[rois.dtype], n, p, b,
              ptr(out), ptr(argmax))
     return (out, argmax) if mode == "max" else out
 
 
 def roi_backward(grad_out, rois, feat_shape, mode="resize", argmax=None):
-    """K-d backward.  grad_out (B,N,P,P,C) f32 -> grad_feat (B,H,W,C) f32 (atomic-free)."""
+    """K-d backward.  grad_out (B,N,P,P,C) f32 -> grad_feat (B,H,W,C) f32 (atomic-free).  Max mode takes the forward's
+    arg-max in either format (int32 flat index or the one-byte compact code)."""
     grad_out = _chk(grad_out, torch.float32, "grad_out", 5)
     rois = _chk(rois, rois.dtype, "rois", 3)
     ctx = get_context(grad_out.device)
     b, h, w, c = feat_shape
     n, p = grad_out.shape[1], grad_out.shape[2]
+    gfeat = ctx.empty((b, h, w, c), torch.float32)
+    if mode == "max" and isinstance(argmax, torch.Tensor) and argmax.dtype == torch.uint8:      # one-byte arg-max
+        argmax = _chk(argmax, torch.uint8, "argmax", 5)
+        ctx.call("frcnn_roi_max_bwd_compact", ptr(grad_out), ptr(rois), _ROI_DTYPES[rois.dtype], ptr(argmax), h, w, c, n, p,
+                 b, ptr(gfeat))
+        return gfeat
     if mode == "max":
         argmax = _chk(argmax, torch.int32, "argmax", 5)
-    gfeat = ctx.empty((b, h, w, c), torch.float32)
     ctx.call("frcnn_roi_bwd", _MODES[mode], ptr(grad_out), ptr(rois), _ROI_DTYPES[rois.dtype],
              ptr(argmax) if mode == "max" else None, h, w, c, n, p, b, ptr(gfeat))
     return gfeat

@@ -195,6 +195,20 @@ FRCNN_API int frcnn_roi_bwd(frcnn_handle* h, void* stream, int mode, const float
                   const void* rois, int roi_dtype, const int32_t* argmax, int height, int width,
                   int channels, int n_rois, int pool, int batch, float* grad_feat);
 
+/* Max mode with a ONE-BYTE arg-max (training fast path: 5 instead of 8 bytes per pooled element leave the forward and
+ * enter the backward).  argmax_u8 [batch,N,P,P,C] u8 = (dy << 4) | dx of the first maximum relative to the bin's first
+ * cell (row floor(ph*h/P), column floor(pw*w/P) of the crop); outputs are identical to frcnn_roi_fwd(MAX), and
+ * y1 + floor(ph*h/P) + dy, x1 + floor(pw*w/P) + dx is the cell frcnn_roi_fwd reports as a flat index.  Available when
+ * frcnn_roi_compact_supported() returns 1: channels % 4 == 0, pool <= 8 and ceil(H/pool)+1, ceil(W/pool)+1 <= 16 (every
+ * bin fits 16 x 16 cells); otherwise FRCNN_ERR_UNSUPPORTED -- use the int32 entry points. */
+FRCNN_API int frcnn_roi_compact_supported(int height, int width, int channels, int pool);
+FRCNN_API int frcnn_roi_max_fwd_compact(frcnn_handle* h, void* stream, const float* feat, int height, int width,
+                              int channels, const void* rois, int roi_dtype, int n_rois, int pool, int batch,
+                              float* out, uint8_t* argmax_u8);
+FRCNN_API int frcnn_roi_max_bwd_compact(frcnn_handle* h, void* stream, const float* grad_out, const void* rois,
+                              int roi_dtype, const uint8_t* argmax_u8, int height, int width, int channels,
+                              int n_rois, int pool, int batch, float* grad_feat);
+
 /* ---- K-e: detector post-processing
  * Replaces the loops of voc_dets.get_dets (voc_dets.py:51-86): per-row argmax
  * class, f64 decode (util.transform, util.py:55-74), x stride, per-class f64

@@ -198,3 +198,66 @@ def test_roi_max_full_size_equals_torchvision_roi_pool(ops):
     want = tv.ops.roi_pool(feat.permute(0, 3, 1, 2).contiguous(), boxes, output_size=7, spatial_scale=1.0)     # (N, C, 7, 7)
     assert torch.equal(out[0], want.permute(0, 2, 3, 1))
     assert torch.equal(torch.gather(feat.reshape(h * w, c), 0, arg.reshape(-1, c).long()).reshape(out.shape), out)
+
+
+def _decode_compact(code, rois, pool, width):
+    """one-byte arg-max (dy << 4 | dx from the bin's first cell) -> flat cell index y*W + x (include/frcnn_b200.h)."""
+    code = code.astype(np.int64)
+    flat = np.zeros(code.shape, np.int64)
+    for r, (x1, y1, x2, y2) in enumerate(np.asarray(rois).tolist()):
+        h, w = y2 - y1, x2 - x1
+        ya = y1 + (np.arange(pool) * h) // pool
+        xa = x1 + (np.arange(pool) * w) // pool
+        flat[r] = (ya[:, None, None] + (code[r] >> 4)) * width + xa[None, :, None] + (code[r] & 15)
+    return flat
+
+
+@pytest.mark.parametrize("b,h,w,c,n,pool", [
+    (2, 12, 17, 64, 40, 7),        # one warp walks every list: backward in the oracle's order
+    (1, 38, 63, 1024, 300, 7),     # C5 map, sliced lists
+    (2, 14, 15, 384, 12, 3),       # pool 3 (bins up to 6 x 6), partial channel slab
+    (1, 38, 94, 256, 64, 7),       # KITTI map: bins up to 7 x 15 cells
+    (1, 10, 13, 8, 9, 8),
+])
+def test_roi_max_compact_argmax(ops, b, h, w, c, n, pool):
+    """Max mode with the one-byte arg-max: same outputs, codes that decode to the oracle's flat arg-max, and the same
+    gradient as the int32 path (bit for bit while one warp walks a block's list, 1e-5 when the lists are sliced)."""
+    import torch
+    assert ops.roi_compact_supported(h, w, c, pool)
+    rng = np.random.default_rng(h * w + n)
+    feat = rng.standard_normal((b, h, w, c), dtype=np.float32)
+    feat[:, ::3, ::2] = feat[0, 0, 0]                              # ties: the first maximum must win
+    rois = np.stack([_rois(rng, n, h, w) for _ in range(b)])
+    rois[0, 0] = [0, 0, w, h]                                      # the largest bins the map allows
+    rois[0, 1] = [w - 1, h - 1, w, h]                              # 1 x 1 crop: every bin repeats the same cell
+    out, code = ops.roi_forward(dev(feat), dev(rois), pool, "max", compact=True)
+    out32, arg32 = ops.roi_forward(dev(feat), dev(rois), pool, "max")
+    assert code.dtype == torch.uint8 and torch.equal(out, out32)
+    for i in range(b):
+        wout, warg = R.roi_max_fwd(feat[i], rois[i], pool)
+        assert np.array_equal(host(out)[i], wout)
+        assert np.array_equal(_decode_compact(host(code)[i], rois[i], pool, w), warg)
+    gout = rng.standard_normal((b, n, pool, pool, c), dtype=np.float32)
+    g8 = ops.roi_backward(dev(gout), dev(rois), (b, h, w, c), "max", argmax=code)
+    g32 = ops.roi_backward(dev(gout), dev(rois), (b, h, w, c), "max", argmax=arg32)
+    if n < 256:                        # one warp per list in both paths: the same additions in the same order
+        assert torch.equal(g8, g32)
+    else:                              # sliced lists: the two paths cut the lists differently (fixed order, re-associated)
+        assert (g8 - g32).abs().max().item() <= 1e-5 * g32.abs().max().item()
+    # the layer picks the compact format by itself
+    from faster_rcnn_b200.custom_layers import roi_pool
+    x = dev(feat).requires_grad_(True)
+    y = roi_pool(x, dev(rois), pool, "max")
+    (y * dev(gout)).sum().backward()
+    assert torch.equal(y.detach(), out) and torch.equal(x.grad, g8)
+
+
+def test_roi_max_compact_unsupported_shapes_fail_loudly(ops):
+    import torch
+    from faster_rcnn_b200 import _lib
+    assert not ops.roi_compact_supported(120, 40, 64, 7)           # bins up to 19 rows
+    assert not ops.roi_compact_supported(38, 63, 6, 7)             # C % 4 != 0
+    with pytest.raises(_lib.FrcnnError) as e:
+        ops.roi_forward(torch.zeros((1, 120, 40, 64), device="cuda"), dev(np.array([[[0, 0, 40, 120]]], np.int16)), 7, "max",
+                        compact=True)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
