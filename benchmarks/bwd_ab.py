@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from faster_rcnn_b200 import ops, synth          # noqa: E402
 from benchmarks.stages import timeit, PEAK       # noqa: E402
 
-KNOBS = ("FRCNN_BWD_IMPL", "FRCNN_BWD_CPB", "FRCNN_BWD_DEPTH", "FRCNN_BWD_PARTS")
+KNOBS = ("FRCNN_BWD_IMPL", "FRCNN_BWD_CPB", "FRCNN_BWD_PARTS")
 
 
 def setenv(cfg):
@@ -35,12 +35,9 @@ def main():
     args = ap.parse_args()
     h, w, c, p = 38, 63, 1024, 7
     variants = {
-        "resize": [{"FRCNN_BWD_IMPL": "cell"}, {},
-                   {"FRCNN_BWD_CPB": 2, "FRCNN_BWD_DEPTH": 4}, {"FRCNN_BWD_CPB": 1, "FRCNN_BWD_DEPTH": 16},
-                   {"FRCNN_BWD_CPB": 1, "FRCNN_BWD_DEPTH": 8}, {"FRCNN_BWD_CPB": 1, "FRCNN_BWD_DEPTH": 4},
+        "resize": [{"FRCNN_BWD_IMPL": "cell"}, {}, {"FRCNN_BWD_CPB": 1},
                    {"FRCNN_BWD_PARTS": 1}, {"FRCNN_BWD_PARTS": 2}, {"FRCNN_BWD_PARTS": 4}, {"FRCNN_BWD_PARTS": 8}],
-        "max": [{"FRCNN_BWD_IMPL": "cell"}, {}, {"FRCNN_BWD_CPB": 2, "FRCNN_BWD_DEPTH": 4},
-                {"FRCNN_BWD_CPB": 1, "FRCNN_BWD_DEPTH": 4},
+        "max": [{"FRCNN_BWD_IMPL": "cell"}, {},
                 {"FRCNN_BWD_PARTS": 1}, {"FRCNN_BWD_PARTS": 2}, {"FRCNN_BWD_PARTS": 4}, {"FRCNN_BWD_PARTS": 8}],
     }
     res = []
@@ -58,7 +55,7 @@ def main():
                 row = {"case": tag, "mode": "maxc_fwd", "ms": round(ms, 4), "frac_5B": round(nb / ms / 1e6 / PEAK, 3)}
                 res.append(row)
                 print(json.dumps(row), flush=True)
-                for cfg in ({}, {"FRCNN_BWD_CPB": 2, "FRCNN_BWD_DEPTH": 4}, {"FRCNN_BWD_CPB": 1, "FRCNN_BWD_DEPTH": 8}):
+                for cfg in ({}, {"FRCNN_BWD_CPB": 1}):
                     setenv(cfg)
                     got = ops.roi_backward(gout, rois, (batch, h, w, c), "max", code)
                     err = (got - want).abs().max().item() / want.abs().max().item()

@@ -547,22 +547,14 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   FRCNN_LAUNCH_CHECK(h, "roi_bwd_mask_kernel");
   FRCNN_LAUNCH_CHECK(h, "roi_bwd_plan_kernel");
 
-  // (channels per lane, ring depth): resize 2 x 8 = 8 KB of dY in flight per warp; max mode carries the arg-max row too
-  int cpb = env_int("FRCNN_BWD_CPB", C >= 256 ? 2 : 1), depth = env_int("FRCNN_BWD_DEPTH", 8);
-  if (mode == FRCNN_ROI_RESIZE) {
-    if (!((cpb == 2 && (depth == 8 || depth == 4)) || (cpb == 1 && (depth == 16 || depth == 8 || depth == 4)))) {
-      cpb = C >= 256 ? 2 : 1;
-      depth = 8;
-    }
-  } else if (compact) {
-    if (!((cpb == 2 && (depth == 4 || depth == 8)) || (cpb == 1 && depth == 8))) {
-      cpb = 1;
-      depth = 8;
-    }
-  } else if (!((cpb == 2 && depth == 4) || (cpb == 1 && (depth == 8 || depth == 4)))) {
-    cpb = 1;
-    depth = 8;
-  }
+  // (channels per lane, ring depth): 2 x 8 = 8 KB of dY in flight per warp where 256 channels exist; the int32 max mode
+  // carries an arg-max row as large as the dY row and keeps 1 x 8 (same-box A/B, benchmarks/bwd_ab.py: C5 x 8 resize
+  // 0.66 ms against 0.68 (2 x 4) / 0.75 (1 x 8) / 0.80 (1 x 16); max 1.32 against 1.30 (2 x 4) / 1.56 (1 x 4);
+  // one-byte arg-max 1.15 (2 x 8) against 1.25 (2 x 4) / 1.40 (1 x 8)).  FRCNN_BWD_CPB=1 selects the narrow variant.
+  int cpb = env_int("FRCNN_BWD_CPB", C >= 256 ? 2 : 1);
+  const int depth = 8;
+  if (cpb != 1 && cpb != 2) cpb = 1;
+  if (mode == FRCNN_ROI_MAX && !compact) cpb = 1;
   const int slabs = (C + cpb * 128 - 1) / (cpb * 128);
   const bool full = C % (cpb * 128) == 0;
   // slices per block: enough warps for ~4 waves of 24 resident warps per SM, at most 8
@@ -584,20 +576,15 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
                                                      W, C, N, P, blocks_x, n_blocks, gfeat)                         \
               : launch_blk_parts<MODE, CPB, D, false>(h, stream, parts, slabs, batch, gout, argmax, tab, eidx, ew,  \
                                                       H, W, C, N, P, blocks_x, n_blocks, gfeat);
+  (void)depth;
   if (mode == FRCNN_ROI_RESIZE) {
-    if (cpb == 2 && depth == 8) { FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 2, 8) }
-    if (cpb == 2 && depth == 4) { FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 2, 4) }
-    if (cpb == 1 && depth == 16) { FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 1, 16) }
-    if (cpb == 1 && depth == 4) { FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 1, 4) }
+    if (cpb == 2) { FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 2, 8) }
     FRCNN_BLK_GO(FRCNN_ROI_RESIZE, 1, 8)
   }
   if (compact) {
-    if (cpb == 2 && depth == 4) { FRCNN_BLK_GO(ROI_MAX_COMPACT, 2, 4) }
-    if (cpb == 2 && depth == 8) { FRCNN_BLK_GO(ROI_MAX_COMPACT, 2, 8) }
+    if (cpb == 2) { FRCNN_BLK_GO(ROI_MAX_COMPACT, 2, 8) }
     FRCNN_BLK_GO(ROI_MAX_COMPACT, 1, 8)
   }
-  if (cpb == 2 && depth == 4) { FRCNN_BLK_GO(FRCNN_ROI_MAX, 2, 4) }
-  if (cpb == 1 && depth == 4) { FRCNN_BLK_GO(FRCNN_ROI_MAX, 1, 4) }
   FRCNN_BLK_GO(FRCNN_ROI_MAX, 1, 8)
 #undef FRCNN_BLK_GO
 }
