@@ -479,9 +479,10 @@ int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, 
   decode_kernel<<<grid, 256, 0, stream>>>(regr, cls, tab, rows, cols, n, keys, boxes,
                                          reinterpret_cast<float4*>(dense_boxes), valid_count);
   FRCNN_LAUNCH_CHECK(h, "decode_kernel");
-  // CTAs per image: as many rank slices as keep the GPU filled in one wave, slices of >= 1024 keys
+  // CTAs per image: as many rank slices as keep the GPU filled in one wave, slices of >= 896 keys (k = 8000 at batch 1:
+  // eight 1000-key slices sorted one key per thread; same-box A/B 38 -> 34 us on clustered scores, equal on uniform ones)
   int splits = 1;
-  while (splits < 8 && (long long)batch * splits * 2 <= h->sm_count && k / (splits * 2) >= 1024) splits <<= 1;
+  while (splits < 8 && (long long)batch * splits * 2 <= h->sm_count && k / (splits * 2) >= 896) splits <<= 1;
   const int slice = (k + splits - 1) / splits + 1;
   auto* ob = reinterpret_cast<BoxI16*>(out_boxes);
   if (slice <= TOPK_THREADS * 1) return launch_topk<1>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
