@@ -200,7 +200,7 @@ FRCNN_API int frcnn_roi_bwd(frcnn_handle* h, void* stream, int mode, const float
  * cell (row floor(ph*h/P), column floor(pw*w/P) of the crop); outputs are identical to frcnn_roi_fwd(MAX), and
  * y1 + floor(ph*h/P) + dy, x1 + floor(pw*w/P) + dx is the cell frcnn_roi_fwd reports as a flat index.  Available when
  * frcnn_roi_compact_supported() returns 1: channels % 4 == 0, pool <= 8 and ceil(H/pool)+1, ceil(W/pool)+1 <= 16 (every
- * bin fits 16 x 16 cells); otherwise FRCNN_ERR_UNSUPPORTED -- use the int32 entry points. */
+ * bin fits 16 x 16 cells) and n_rois < 65536; otherwise FRCNN_ERR_UNSUPPORTED -- use the int32 entry points. */
 FRCNN_API int frcnn_roi_compact_supported(int height, int width, int channels, int pool);
 FRCNN_API int frcnn_roi_max_fwd_compact(frcnn_handle* h, void* stream, const float* feat, int height, int width,
                               int channels, const void* rois, int roi_dtype, int n_rois, int pool, int batch,
