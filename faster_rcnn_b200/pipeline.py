@@ -125,8 +125,9 @@ class ProposalRoiPipeline:
         self._copy_stream.wait_stream(cur)            # the previous call's kernels no longer read the buffers
         events = []
         # chunked upload hides the 10 MB/image feature copy behind the kernels; with the features already on the device
-        # only 0.4 MB/image of head outputs moves, and one launch sequence over the whole batch is faster
-        step = b if feat_on_device else max(1, int(self.h2d_chunk))
+        # only 0.4 MB/image of head outputs moves: a few large chunks keep that copy off the critical path without paying
+        # the small-batch latency of the proposal kernels
+        step = max(16, -(-b // 4)) if feat_on_device else max(1, int(self.h2d_chunk))
         with torch.cuda.stream(self._copy_stream):
             for lo in range(0, b, step):
                 hi = min(b, lo + step)
