@@ -241,36 +241,47 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
     }
     const unsigned ball = __ballot_sync(0xffffffffu, sup);
     if (lane == 0) sup_part[warp] = ball;
-    // (b) intra-tile row masks: thread -> row i = tid/8, eight columns j = (tid%8)*8 ..
+    // (b) intra-tile row masks, triangular: only the 2016 pairs i < j exist.  Rows p and 63 - p together have 63 of them;
+    // 16 threads share such a row pair, four pairs each, so every warp runs four pair tests per thread instead of the
+    // eight (half of them masked off) of a square 64 x 64 mapping.
     {
-      const int i = tid >> 3, j0 = (tid & 7) * 8;
-      unsigned lo = 0, hi = 0;
-      if (i < tile_n) {
-        const BoxI16 a = sorted[base + i];
-        const int a_area = (a.x2 - a.x1 + 1) * (a.y2 - a.y1 + 1);
+      const int p = tid >> 4, e0 = (tid & 15) * 4, n1 = 63 - p;
+      const BoxI16 a1 = sorted[base + min(p, tile_n - 1)], a2 = sorted[base + min(63 - p, tile_n - 1)];
+      const int a1_area = (a1.x2 - a1.x1 + 1) * (a1.y2 - a1.y1 + 1), a2_area = (a2.x2 - a2.x1 + 1) * (a2.y2 - a2.y1 + 1);
+      unsigned lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j = j0 + jj;
-          if (j > i && j < tile_n) {
-            const BoxI16 c = sorted[base + j];
-            const int c_area = (c.x2 - c.x1 + 1) * (c.y2 - c.y1 + 1);
-            bool hit;
-            if (rat_q > 0) {
-              const int r = screen_rational(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, rat_p, rat_q);
-              hit = r == 1 || (r == 2 && suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives));
-            } else {
-              hit = suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives);
-            }
-            if (hit) {
-              if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
-            }
+      for (int ee = 0; ee < 4; ++ee) {
+        const int e = e0 + ee;
+        const bool first = e < n1;                     // pair of row p, else of row 63 - p
+        const int j = first ? p + 1 + e : 64 - p + (e - n1);
+        if (e < 63 && j < tile_n) {                    // i < j by construction
+          const BoxI16 a = first ? a1 : a2;
+          const int a_area = first ? a1_area : a2_area;
+          const BoxI16 c = sorted[base + j];
+          const int c_area = (c.x2 - c.x1 + 1) * (c.y2 - c.y1 + 1);
+          bool hit;
+          if (rat_q > 0) {
+            const int r = screen_rational(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, rat_p, rat_q);
+            hit = r == 1 || (r == 2 && suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives));
+          } else {
+            hit = suppressed_i16(a.x1, a.y1, a.x2, a.y2, a_area, c.x1, c.y1, c.x2, c.y2, c_area, t_f, thresh, zero_survives);
+          }
+          if (hit) {
+            const unsigned bit = 1u << (j & 31);
+            if (first) { if (j < 32) lo1 |= bit; else hi1 |= bit; }
+            else       { if (j < 32) lo2 |= bit; else hi2 |= bit; }
           }
         }
       }
-      const unsigned gmask = 0xffu << (lane & 24);
-      lo = __reduce_or_sync(gmask, lo);
-      hi = __reduce_or_sync(gmask, hi);
-      if ((tid & 7) == 0) row_mask[i] = ((unsigned long long)hi << 32) | lo;
+      const unsigned gmask = 0xffffu << (lane & 16);
+      lo1 = __reduce_or_sync(gmask, lo1);
+      hi1 = __reduce_or_sync(gmask, hi1);
+      lo2 = __reduce_or_sync(gmask, lo2);
+      hi2 = __reduce_or_sync(gmask, hi2);
+      if ((tid & 15) == 0) {
+        row_mask[p] = ((unsigned long long)hi1 << 32) | lo1;
+        row_mask[63 - p] = ((unsigned long long)hi2 << 32) | lo2;
+      }
     }
     __syncthreads();
     // exchange the partial masks inside the cluster (distributed shared memory)
