@@ -87,6 +87,30 @@ __device__ __forceinline__ int screen_rational(int ax1, int ay1, int ax2, int ay
   return uni > 0 ? (over ? 1 : 0) : 2;
 }
 
+// The same test with 32-bit products, for images whose boxes are small enough that neither product can overflow
+// (3 * maxdim^2 * max(p, q) < 2^31, checked once per image): two IMADs and one compare instead of two wide multiplies
+// and a 64-bit compare.  The kept-list sweep is issue-bound, every instruction of the pair test counts.
+__device__ __forceinline__ int screen_rational32(int ax1, int ay1, int ax2, int ay2, int a_area, int bx1, int by1,
+                                                 int bx2, int by2, int b_area, int p, int q) {
+  const int iw = min(ax2, bx2) - max(ax1, bx1) + 1;
+  const int ih = min(ay2, by2) - max(ay1, by1) + 1;
+  const int inter = max(iw, 0) * max(ih, 0);
+  const int uni = a_area + b_area - inter;
+  const bool over = inter * q > uni * p;
+  return uni > 0 ? (over ? 1 : 0) : 2;
+}
+
+// ... and when, in addition, every box of the image is valid (x2 >= x1, y2 >= y1: union > 0 always, no "uncertain" case):
+// inter*q > (A + B - inter)*p  <=>  inter*(p+q) - A*p > B*p.  The kept list then stores -A*p instead of A and the
+// candidate carries B*p: one IMAD and one compare after the intersection (12 ALU instructions per pair in all).
+__device__ __forceinline__ bool screen_small_valid(int ax1, int ay1, int ax2, int ay2, int neg_ap, int bx1, int by1,
+                                                   int bx2, int by2, int bp, int pq) {
+  const int iw = min(ax2, bx2) - max(ax1, bx1) + 1;
+  const int ih = min(ay2, by2) - max(ay1, by1) + 1;
+  const int inter = max(iw, 0) * max(ih, 0);
+  return inter * pq + neg_ap > bp;
+}
+
 // Thread-block clusters: an image may be given a cluster of CL CTAs (1, 2, 4, 8 or 16 SMs).  Every CTA
 // holds the full candidate array, the kept list is dealt round-robin over the CTAs (kept j lives in CTA
 // j % CL), each CTA tests the tile's 64 candidates against ITS share, the 64-bit partial masks are
@@ -116,7 +140,7 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
   __shared__ unsigned sup_part[NMS_THREADS / 32];
   __shared__ unsigned long long s_xpart[2][16];      // [tile parity][cluster rank] partial "suppressed by kept" masks
   __shared__ unsigned long long s_keepbits;
-  __shared__ int s_unsorted, s_nkept, s_stop;
+  __shared__ int s_unsorted, s_nkept, s_stop, s_maxdim;
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (cl > 1) ? (int)cluster.block_rank() : 0;
@@ -126,7 +150,7 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
   const float* scores = scores_all + (size_t)img * n_max;
   int* order = order_all + ((size_t)img * cl + rank) * n_max;     // per-CTA scratch (only rank 0's is read back)
 
-  if (tid == 0) { s_unsorted = 0; s_nkept = 0; s_stop = 0; }
+  if (tid == 0) { s_unsorted = 0; s_nkept = 0; s_stop = 0; s_maxdim = 0; }
   __syncthreads();
   // distributed shared memory may only be touched once every CTA of the cluster is running
   if (cl > 1) cluster.sync();
@@ -200,6 +224,21 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
   const int slice = tid >> 6;                       // NMS_THREADS / NMS_TILE = 8 slices of the kept list
   constexpr int SLICES = NMS_THREADS / NMS_TILE;
 
+  // largest box edge of the image -> may the pair test use 32-bit products?
+  {
+    int md = 0;
+    for (int i = tid; i < n; i += NMS_THREADS) {
+      const BoxI16 b = sorted[i];
+      md = max(md, max(abs(b.x2 - b.x1), abs(b.y2 - b.y1)) + 1);
+      if (b.x2 < b.x1 || b.y2 < b.y1) md = 1 << 20;          // an invalid box switches both fast paths off
+    }
+    md = __reduce_max_sync(0xffffffffu, md);
+    if (lane == 0) atomicMax(&s_maxdim, md);
+  }
+  __syncthreads();
+  const bool small = rat_q > 0 && 3.0 * (double)s_maxdim * (double)s_maxdim * (double)max(rat_p, rat_q) < 2147483647.0;
+  const bool small_valid = small && s_maxdim < (1 << 20);     // kept_area then holds -area * p (see screen_small_valid)
+
   int parity = 0;
   for (int base = 0; base < n; base += NMS_TILE, parity ^= 1) {
     const int tile_n = min(NMS_TILE, n - base);
@@ -213,7 +252,22 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
     bool sup = false;
     if (fast_ok) {
       int flags = 0;                               // bit0: suppressed by some kept box, bit1: some test uncertain
-      if (rat_q > 0) {
+      if (small_valid) {
+        const int bp = b_area * rat_p, pq = rat_p + rat_q;
+        bool hit = false;
+#pragma unroll 4
+        for (int j = slice; j < nlocal; j += SLICES) {
+          const int4 kb = kept_box[j];
+          hit |= screen_small_valid(kb.x, kb.y, kb.z, kb.w, kept_area[j], bx1, by1, bx2, by2, bp, pq);
+        }
+        flags = hit ? 1 : 0;
+      } else if (small) {
+#pragma unroll 4
+        for (int j = slice; j < nlocal; j += SLICES) {
+          const int4 kb = kept_box[j];
+          flags |= screen_rational32(kb.x, kb.y, kb.z, kb.w, kept_area[j], bx1, by1, bx2, by2, b_area, rat_p, rat_q);
+        }
+      } else if (rat_q > 0) {
 #pragma unroll 4
         for (int j = slice; j < nlocal; j += SLICES) {
           const int4 kb = kept_box[j];
@@ -346,7 +400,7 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
       const int slot = nkept + __popcll(keepbits & ((1ull << tid) - 1ull));
       if (slot % cl == rank) {
         kept_box[slot / cl] = make_int4(bx1, by1, bx2, by2);      // tid < 64 => cand == tid
-        kept_area[slot / cl] = b_area;
+        kept_area[slot / cl] = small_valid ? -(b_area * rat_p) : b_area;
       }
       kept_slot[slot] = base + tid;
     }
