@@ -140,7 +140,7 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
   __shared__ unsigned sup_part[NMS_THREADS / 32];
   __shared__ unsigned long long s_xpart[2][16];      // [tile parity][cluster rank] partial "suppressed by kept" masks
   __shared__ unsigned long long s_keepbits;
-  __shared__ int s_unsorted, s_nkept, s_stop, s_maxdim;
+  __shared__ int s_unsorted, s_nkept, s_stop, s_maxdim, s_maxabs;
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (cl > 1) ? (int)cluster.block_rank() : 0;
@@ -150,7 +150,7 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
   const float* scores = scores_all + (size_t)img * n_max;
   int* order = order_all + ((size_t)img * cl + rank) * n_max;     // per-CTA scratch (only rank 0's is read back)
 
-  if (tid == 0) { s_unsorted = 0; s_nkept = 0; s_stop = 0; s_maxdim = 0; }
+  if (tid == 0) { s_unsorted = 0; s_nkept = 0; s_stop = 0; s_maxdim = 0; s_maxabs = 0; }
   __syncthreads();
   // distributed shared memory may only be touched once every CTA of the cluster is running
   if (cl > 1) cluster.sync();
@@ -226,18 +226,25 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
 
   // largest box edge of the image -> may the pair test use 32-bit products?
   {
-    int md = 0;
+    int md = 0, ac = 0;
     for (int i = tid; i < n; i += NMS_THREADS) {
       const BoxI16 b = sorted[i];
       md = max(md, max(abs(b.x2 - b.x1), abs(b.y2 - b.y1)) + 1);
+      ac = max(ac, max(max(abs((int)b.x1), abs((int)b.y1)), max(abs((int)b.x2), abs((int)b.y2))));
       if (b.x2 < b.x1 || b.y2 < b.y1) md = 1 << 20;          // an invalid box switches both fast paths off
     }
     md = __reduce_max_sync(0xffffffffu, md);
-    if (lane == 0) atomicMax(&s_maxdim, md);
+    ac = __reduce_max_sync(0xffffffffu, ac);
+    if (lane == 0) { atomicMax(&s_maxdim, md); atomicMax(&s_maxabs, ac); }
   }
   __syncthreads();
   const bool small = rat_q > 0 && 3.0 * (double)s_maxdim * (double)s_maxdim * (double)max(rat_p, rat_q) < 2147483647.0;
   const bool small_valid = small && s_maxdim < (1 << 20);     // kept_area then holds -area * p (see screen_small_valid)
+  // ... and with coordinates below 16000 both corner pairs live in one register each and the intersection is three
+  // packed 16-bit DPX instructions: (-max x1, -max y1) = VIMNMX.S16x2 of the negated lows, (min x2+1, min y2+1) =
+  // VIMNMX.S16x2, (iw, ih) = relu(sum) = VIADDMNMX.S16x2.RELU; 8 ALU instructions per pair.  kept_box then holds
+  // (pack(-x1,-y1), pack(x2+1,y2+1), -area*p, -) -- one 128-bit load per pair and no kept_area load.
+  const bool packed = small_valid && s_maxabs < 16000;
 
   int parity = 0;
   for (int base = 0; base < n; base += NMS_TILE, parity ^= 1) {
@@ -252,7 +259,19 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
     bool sup = false;
     if (fast_ok) {
       int flags = 0;                               // bit0: suppressed by some kept box, bit1: some test uncertain
-      if (small_valid) {
+      if (packed) {
+        const int bp = b_area * rat_p, pq = rat_p + rat_q;
+        const unsigned nb_lo = ((unsigned)(-bx1) & 0xffffu) | ((unsigned)(-by1) << 16);
+        const unsigned b_hi = ((unsigned)(bx2 + 1) & 0xffffu) | ((unsigned)(by2 + 1) << 16);
+        bool hit = false;
+#pragma unroll 4
+        for (int j = slice; j < nlocal; j += SLICES) {
+          const int4 kb = kept_box[j];
+          const unsigned d = __viaddmax_s16x2_relu(__vmins2((unsigned)kb.y, b_hi), __vmins2((unsigned)kb.x, nb_lo), 0u);
+          hit |= (int)(d & 0xffffu) * (int)(d >> 16) * pq + kb.z > bp;
+        }
+        flags = hit ? 1 : 0;
+      } else if (small_valid) {
         const int bp = b_area * rat_p, pq = rat_p + rat_q;
         bool hit = false;
 #pragma unroll 4
@@ -399,7 +418,11 @@ nms_i16_kernel(const BoxI16* __restrict__ boxes_all, const float* __restrict__ s
     if (tid < NMS_TILE && ((keepbits >> tid) & 1ull)) {
       const int slot = nkept + __popcll(keepbits & ((1ull << tid) - 1ull));
       if (slot % cl == rank) {
-        kept_box[slot / cl] = make_int4(bx1, by1, bx2, by2);      // tid < 64 => cand == tid
+        if (packed)                                               // tid < 64 => cand == tid
+          kept_box[slot / cl] = make_int4((int)(((unsigned)(-bx1) & 0xffffu) | ((unsigned)(-by1) << 16)),
+                                          (int)(((unsigned)(bx2 + 1) & 0xffffu) | ((unsigned)(by2 + 1) << 16)), -(b_area * rat_p), 0);
+        else
+          kept_box[slot / cl] = make_int4(bx1, by1, bx2, by2);
         kept_area[slot / cl] = small_valid ? -(b_area * rat_p) : b_area;
       }
       kept_slot[slot] = base + tid;
