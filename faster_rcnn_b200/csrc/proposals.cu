@@ -1,361 +1,567 @@
-// K-a: anchors + delta decode + sanitize + validity filter + radix-select top-k + sort.
+// K-a: anchors + delta decode + sanitize + validity filter + exact top-k in sorted order, ONE kernel.
 //
-// Kernel 1 (decode_kernel): one thread per anchor, fully parallel over (anchor, image).
-//   Reads regr (16 B) + cls (4 B), writes one 64-bit sort key and one packed int16x4 box
-//   (16 B) per anchor.  HBM-bound, coalesced 128-bit loads/stores.
-// Kernel 2 (topk_kernel): one CTA per image.  MSB-first 11-bit radix select over the
-//   64-bit keys (unique because the anchor index is part of the key) finds the exact
-//   k-th largest key, survivors are compacted into shared memory, sorted descending with a
-//   register-blocked bitonic network and gathered into the output arrays.
+// proposals_kernel: a thread-block cluster of `splits` CTAs per image.
+//   1. decode   every CTA decodes 1/splits of the image's anchors (regr 16 B + cls 4 B in, 64-bit sort key + int16x4 box
+//               out, L2-resident) and histograms its keys by a 2048-bucket monotone digit in shared memory;
+//   2. exchange the per-CTA histograms are summed through distributed shared memory (reduce-scatter + all-gather, two
+//               cluster barriers), so every CTA knows how many keys each bucket holds in the whole image;
+//   3. slice    CTA r owns the ranks [r*k/splits, (r+1)*k/splits) of the descending order.  The buckets of its two
+//               bounds follow from the histogram; ONE sweep over the image's keys sends every key strictly between the
+//               two boundary buckets into the slice and parks the boundary buckets' keys in a shared-memory stash, where
+//               the two exact splitters are found together (11-bit radix passes, both selects share one packed histogram);
+//   4. sort     the <= 2047 keys of the slice are sorted by 256 threads holding E keys each in registers (bitonic
+//               network: strides < E are register swaps, < 32E warp shuffles, only >= 32E go through shared memory);
+//   5. gather   boxes / scores / indices of the slice are written at their final ranks.  Slices need no merge.
+// The bucket digit is the key's top 15 bits (sign, exponent, 6 mantissa bits) taken relative to 1.0 and clamped, i.e. 64
+// buckets per octave over [2^-32, 1): objectness scores are sigmoid outputs, and the plain top-11-bit digit of round 1
+// resolves them into four buckets per octave only (2700-key boundary buckets on uniform scores).  Scores outside the
+// window land in the two clamped end buckets; a bound that falls into one of those, or boundary buckets that outgrow
+// the stash (massive ties), takes the fall-back: exact radix selects over all keys of the image (several sweeps).
 //
 // Reference semantics (file:line under /root/reference/faster_rcnn):
 //   det_util.py:162-175 anchors (centre = cell index, x1 = x - w//2, x2 = x1 + w)
 //   util.py:111-142     float32 decode, separate roundings (this TU is built with -fmad=false)
 //   det_util.py:179-192 sanitize order, :196-205 validity, :68-76/:147-155 sort + top-k + int16
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace frcnn {
 
 struct __align__(8) BoxI16 { short x1, y1, x2, y2; };
 
-constexpr int TOPK_THREADS = 1024;
-constexpr int TOPK_WARPS = TOPK_THREADS / 32;
-constexpr int TOPK_BITS = 11;                       // radix-select digit width
+constexpr int TOPK_BITS = 11;                       // radix digit width
 constexpr int TOPK_BINS = 1 << TOPK_BITS;
-constexpr int TOPK_META = TOPK_BINS + 1;            // per image: [valid count, histogram of the keys' top 11 bits]
+constexpr int TOPK_U = 8;                           // keys fetched per thread before any is consumed (hides the L2 latency)
+constexpr int SORT_T = 256;                         // threads of a CTA that run the sorting network
+constexpr int FINE_SHIFT = 49;                      // bucket digit = key bits 63..49 ...
+constexpr int FINE_BASE = 0x5FC0 - (TOPK_BINS - 1); // ... minus this, clamped to [0, 2047]; 0x5FC0 = those bits of 1.0f
+constexpr int MAX_SPLITS = 16;                      // cluster size limit (non-portable above 8)
 
-__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ regr,
-                                                     const float* __restrict__ cls, AnchorTable tab,
-                                                     int rows, int cols, int n_per_image,
-                                                     unsigned long long* __restrict__ keys,
-                                                     BoxI16* __restrict__ boxes,
-                                                     float4* __restrict__ dense,
-                                                     int* __restrict__ valid_count) {
-  const int img = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = false;
-  unsigned digit = 0xffffffffu;
-  if (i < n_per_image) {
-    const size_t g = (size_t)img * n_per_image + i;
-    const int a = i % tab.n;
-    const int loc = i / tab.n;
-    const int cx_i = loc % cols, cy_i = loc / cols;
-    const int aw = tab.w[a], ah = tab.h[a];
-
-    // anchors are integer valued -> exact in float32
-    float x = (float)(cx_i - (aw >> 1));
-    float y = (float)(cy_i - (ah >> 1));
-    float w = (float)aw;     // (x + aw) - x
-    float hgt = (float)ah;
-
-    const float4 r = ldg_f4(regr + 4 * g);
-    const float tx = __fdiv_rn(r.x, 10.0f), ty = __fdiv_rn(r.y, 10.0f);
-    const float tw = __fdiv_rn(r.z, 5.0f), th = __fdiv_rn(r.w, 5.0f);
-
-    x = __fadd_rn(x, __fdiv_rn(w, 2.0f));
-    y = __fadd_rn(y, __fdiv_rn(hgt, 2.0f));
-    x = __fadd_rn(x, __fmul_rn(tx, w));
-    y = __fadd_rn(y, __fmul_rn(ty, hgt));
-    w = __fmul_rn(w, np_expf(tw));
-    hgt = __fmul_rn(hgt, np_expf(th));
-    x = __fsub_rn(x, __fdiv_rn(w, 2.0f));
-    y = __fsub_rn(y, __fdiv_rn(hgt, 2.0f));
-    x = rintf(x); y = rintf(y); w = rintf(w); hgt = rintf(hgt);     // np.round: half to even
-    float x2 = __fadd_rn(w, x), y2 = __fadd_rn(hgt, y);
-
-    x2 = np_max(__fadd_rn(x, 1.0f), x2);
-    y2 = np_max(__fadd_rn(y, 1.0f), y2);
-    x = np_max(0.0f, x);
-    y = np_max(0.0f, y);
-    x2 = np_min((float)(cols - 1), x2);
-    y2 = np_min((float)(rows - 1), y2);
-
-    if (dense) dense[g] = make_float4(x, y, x2, y2);
-
-    valid = (x2 > x) && (y2 > y);
-    unsigned long long key = 0ull;
-    BoxI16 b = {0, 0, 0, 0};
-    if (valid) {
-      key = ((unsigned long long)mono_key(__ldg(cls + g)) << 32) | (unsigned)i;
-      b.x1 = (short)(int)x; b.y1 = (short)(int)y; b.x2 = (short)(int)x2; b.y2 = (short)(int)y2;
-    }
-    keys[g] = key;
-    boxes[g] = b;
-    digit = valid ? (unsigned)(key >> (64 - TOPK_BITS)) : 0xffffffffu;
-  }
-  // first pass of top-k's radix select, done here while the key is in a register: histogram of the top 11 bits
-  // (a handful of distinct digits per warp -> one aggregated atomic per digit)
-  int* meta = valid_count + (size_t)img * TOPK_META;
-  const unsigned peers = __match_any_sync(0xffffffffu, digit);
-  if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(meta + 1 + digit, __popc(peers));
-  // number of valid anchors of the image (top-k needs it): one atomic per CTA
-  const int nv = __syncthreads_count(valid);
-  if (threadIdx.x == 0 && nv) atomicAdd(meta, nv);
+__device__ __forceinline__ int fine_digit(unsigned long long key) {
+  const int d = (int)(key >> FINE_SHIFT) - FINE_BASE;
+  return min(max(d, 0), TOPK_BINS - 1);
+}
+__device__ __forceinline__ unsigned long long fine_prefix(int digit) {
+  return (unsigned long long)(digit + FINE_BASE) << FINE_SHIFT;
 }
 
+// unsigned division by a launch-time constant (Granlund-Montgomery round-up form, exact for all 32-bit numerators)
+struct FastDiv { unsigned m, s1, s2; };
+static FastDiv make_fastdiv(unsigned d) {
+  FastDiv f = {0u, 0u, 0u};
+  if (d <= 1) return f;
+  unsigned l = 0;
+  while ((1ull << l) < d) ++l;
+  f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = 1;
+  f.s2 = l - 1;
+  return f;
+}
+__device__ __forceinline__ unsigned fast_div(unsigned i, FastDiv f) {
+  const unsigned t = __umulhi(f.m, i);
+  return (t + ((i - t) >> f.s1)) >> f.s2;
+}
 
-// block-wide inclusive scan of one int per thread (1024 threads); `warp_tot` is [TOPK_WARPS] shared
-__device__ __forceinline__ int block_inclusive_scan(int v, int* warp_tot) {
+// np_expf (common.cuh) without branches: the three special ranges become selects and the final scaling by 2^q is two
+// multiplications by exact powers of two (one rounding, like scalbnf; |q| <= 150 inside the evaluated range).
+__device__ __forceinline__ float np_expf_inline(float x) {
+  float q = __fmul_rn(x, 1.44269504088896340736f);
+  q = __fsub_rn(__fadd_rn(q, 12582912.0f), 12582912.0f);
+  float r = __fmaf_rn(q, -6.93145752e-1f, x);
+  r = __fmaf_rn(q, -1.42860677e-6f, r);
+  float num = __fmaf_rn(5.082762527590693718096e-04f, r, 6.757896990527504603057e-03f);
+  num = __fmaf_rn(num, r, 5.114512081637298353406e-02f);
+  num = __fmaf_rn(num, r, 2.473615434895520810817e-01f);
+  num = __fmaf_rn(num, r, 7.257664613233124478488e-01f);
+  num = __fmaf_rn(num, r, 9.999999999980870924916e-01f);
+  float den = __fmaf_rn(2.159509375685829852307e-02f, r, -2.742335390411667452936e-01f);
+  den = __fmaf_rn(den, r, 1.0f);
+  float v = __fdiv_rn(num, den);
+  const int qi = (int)q, h1 = qi >> 1, h2 = qi - h1;
+  v = __fmul_rn(__fmul_rn(v, __int_as_float((h1 + 127) << 23)), __int_as_float((h2 + 127) << 23));
+  v = x > 88.72283935546875f ? __int_as_float(0x7f800000) : v;
+  v = x < -103.97208404541015625f ? 0.0f : v;
+  return x != x ? x : v;
+}
+
+// np.maximum / np.minimum (NaN-propagating) as single instructions
+__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+// x / D by the reciprocal-and-residual form of div_const (common.cuh), without its range guard
+template <int D>
+__device__ __forceinline__ float div_const_core(float x) {
+  const float c = 1.0f / (float)D;
+  const float q0 = __fmul_rn(x, c);
+  return __fmaf_rn(__fmaf_rn(-(float)D, q0, x), c, q0);
+}
+
+__device__ __forceinline__ void st_shared_u64(unsigned addr, unsigned long long v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ int atom_shared_add(unsigned addr, int v) {
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+
+// block-wide inclusive scan of one value per thread with ONE barrier: every warp scans the warp totals itself.
+// `warp_tot` is [2][32] shared, `phase` alternates between the halves so that back-to-back calls need no second barrier.
+template <int THREADS>
+__device__ __forceinline__ unsigned block_inclusive_scan(unsigned v, unsigned (*warp_tot)[32], int& phase) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const int u = __shfl_up_sync(0xffffffffu, v, d);
+    const unsigned u = __shfl_up_sync(0xffffffffu, v, d);
     if (lane >= d) v += u;
   }
-  if (lane == 31) warp_tot[warp] = v;
+  if (lane == 31) warp_tot[phase][warp] = v;
   __syncthreads();
-  if (warp == 0) {
-    int w = warp_tot[lane];
+  unsigned w = lane < THREADS / 32 ? warp_tot[phase][lane] : 0u;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, w, d);
-      if (lane >= d) w += u;
-    }
-    warp_tot[lane] = w;
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, w, d);
+    if (lane >= d) w += u;
   }
-  __syncthreads();
-  const int before = warp ? warp_tot[warp - 1] : 0;
-  __syncthreads();                                   // warp_tot is reused by the next call
-  return v + before;
+  const unsigned before = __shfl_sync(0xffffffffu, w, (warp + 31) & 31);
+  phase ^= 1;
+  return v + (warp ? before : 0u);
 }
 
-// shared-memory slot of logical element e: one pad entry per E elements keeps the blocked
-// register <-> shared transfers (thread t owns e = t*E .. t*E+E-1) at the 2-way minimum of 64-bit accesses
-template <int E>
-__device__ __forceinline__ int pad_slot(int e) { return e + e / E; }
-
-// Block-wide exact selection of up to TWO ranks in one set of sweeps: splitter T_s such that exactly `rank_s` keys are
-// >= T_s (keys are unique and non-zero; the caller guarantees 0 < rank < number of valid keys).  MSB-first radix
-// select, 11-bit digits, shared histograms fed by warp-aggregated atomics (__match_any_sync: one atomic per distinct
-// digit per warp), suffix scan over the bins.  The pass at which a splitter's bucket holds exactly the keys still
-// needed ends that select (3 passes for tie-free float scores).  A CTA in the middle of the rank range needs both of
-// its slice bounds; selecting them jointly reads the keys once per pass instead of twice, and while the two prefixes
-// still agree (always in the first pass) one histogram serves both.
-// Keys are fetched 8 per thread before any is consumed, which hides the L2 latency.
-constexpr int TOPK_U = 8;
-__device__ void radix_select2(const unsigned long long* __restrict__ keys, const int* __restrict__ g_hist1, int n,
-                              int rank_a, int rank_b, bool use_b,
-                              unsigned* hist /* [2][TOPK_BINS] */, int* warp_tot, unsigned long long* s_prefix /* [2] */,
-                              int* s_need /* [2] */, int* s_done /* [2] */, unsigned long long& t_a,
-                              unsigned long long& t_b) {
+// Suffix scan over a TOPK_BINS histogram (bins counted from the top) and up to two look-ups in it: the bin that holds
+// the need-th largest element (1-based), written as out[3*s + {0,1,2}] = {bin, rank of that element inside the bin,
+// size of the bin}.  PACKED: the histogram carries two 16-bit counts per word (select 0 in the low half, 1 in the high
+// half; no half exceeds 65535 in total), otherwise both look-ups read the whole word.  Block-wide, ends with a barrier.
+template <int THREADS, bool PACKED>
+__device__ __forceinline__ void hist_lookup2(const unsigned* hh, int need0, bool use0, int need1, bool use1,
+                                             unsigned (*warp_tot)[32], int& phase, int* out) {
+  constexpr int BPT = TOPK_BINS / THREADS;
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    s_prefix[0] = s_prefix[1] = 0ull;
-    s_need[0] = rank_a; s_need[1] = rank_b;
-    s_done[0] = 0; s_done[1] = use_b ? 0 : 1;
+  unsigned c[BPT], sum = 0u;
+#pragma unroll
+  for (int j = 0; j < BPT; ++j) { c[j] = hh[TOPK_BINS - 1 - BPT * tid - j]; sum += c[j]; }
+  const unsigned incl = block_inclusive_scan<THREADS>(sum, warp_tot, phase);
+  const unsigned excl = incl - sum;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!(s ? use1 : use0)) continue;
+    const int need = s ? need1 : need0;
+    const int lo = PACKED ? (int)(s ? excl >> 16 : excl & 0xffffu) : (int)excl;
+    const int hi = PACKED ? (int)(s ? incl >> 16 : incl & 0xffffu) : (int)incl;
+    if (lo < need && need <= hi) {                   // exactly one thread
+      int e = lo;
+#pragma unroll
+      for (int j = 0; j < BPT; ++j) {
+        const int cj = PACKED ? (int)(s ? c[j] >> 16 : c[j] & 0xffffu) : (int)c[j];
+        if (need > e && need <= e + cj) { out[3 * s] = TOPK_BINS - 1 - BPT * tid - j; out[3 * s + 1] = need - e; out[3 * s + 2] = cj; }
+        e += cj;
+      }
+    }
   }
   __syncthreads();
-  for (int hi = 64; hi > 0;) {
-    const int bits = hi < TOPK_BITS ? hi : TOPK_BITS;
-    const int shift = hi - bits;
-    for (int i = tid; i < 2 * TOPK_BINS; i += TOPK_THREADS) hist[i] = 0u;
+}
+
+// Fall-back: exact selection over all keys of the image, the key T with exactly `need` valid keys >= T (keys are unique
+// and non-zero; 0 < need <= number of valid keys).  MSB-first radix select, one sweep per 11-bit digit.
+template <int THREADS>
+__device__ unsigned long long radix_select_global(const unsigned long long* keys, int n, int need, unsigned* hist,
+                                                  unsigned (*warp_tot)[32], int& phase, int* s_out) {
+  unsigned long long prefix = 0ull;
+  int hi = 64;
+  while (true) {
+    const int bits = hi < TOPK_BITS ? hi : TOPK_BITS, shift = hi - bits;
+    for (int i = threadIdx.x; i < TOPK_BINS; i += THREADS) hist[i] = 0u;
     __syncthreads();
-    const unsigned long long pa = s_prefix[0], pb = s_prefix[1];
-    const bool da = s_done[0] != 0, db = s_done[1] != 0;
-    const bool same = !da && !db && (hi == 64 || (pa >> hi) == (pb >> hi));   // identical histograms: build A's only
-    if (hi == 64) {                                  // first pass: decode_kernel already histogrammed the top bits
-      for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = (unsigned)__ldg(g_hist1 + i);
-    } else
-    for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
+    for (int base = 0; base < n; base += THREADS * TOPK_U) {
       unsigned long long kk[TOPK_U];
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
-        const int i = base + u * TOPK_THREADS + tid;
-        kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
+        const int i = base + u * THREADS + (int)threadIdx.x;
+        kk[u] = (i < n) ? __ldcg(keys + i) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
         const unsigned long long key = kk[u];
-        const bool in_a = !da && key != 0ull && (hi == 64 || (key >> hi) == (pa >> hi));
-        const unsigned digit = (unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u));
-        if (in_a) atomicAdd(&hist[digit], 1u);       // few keys are left after the first pass and their digits are spread out
-        if (!db && !same && key != 0ull && (key >> hi) == (pb >> hi)) atomicAdd(&hist[TOPK_BINS + digit], 1u);
+        if (key != 0ull && (hi == 64 || (key >> hi) == (prefix >> hi)))
+          atomicAdd(&hist[(unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u))], 1u);
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int sel = 0; sel < 2; ++sel) {
-      if (sel == 0 ? da : db) continue;              // block-uniform
-      const unsigned* hh = hist + ((sel == 1 && !same) ? TOPK_BINS : 0);
-      const unsigned long long prefix = sel == 0 ? pa : pb;
-      const int need = s_need[sel];
-      // suffix scan from the top bin: thread t owns bins BINS-1-2t (c0) and BINS-2-2t (c1)
-      const int c0 = (int)hh[TOPK_BINS - 1 - 2 * tid], c1 = (int)hh[TOPK_BINS - 2 - 2 * tid];
-      const int incl = block_inclusive_scan(c0 + c1, warp_tot);
-      const int excl = incl - c0 - c1;
-      int d = -1, rest = 0, cnt = 0;
-      if (excl < need && excl + c0 >= need) { d = TOPK_BINS - 1 - 2 * tid; rest = need - excl; cnt = c0; }
-      else if (excl + c0 < need && incl >= need) { d = TOPK_BINS - 2 - 2 * tid; rest = need - excl - c0; cnt = c1; }
-      if (d >= 0) {                                  // exactly one thread
-        s_prefix[sel] = prefix | ((unsigned long long)d << shift);
-        s_need[sel] = rest;
-        if (shift == 0 || cnt == rest) s_done[sel] = 1;   // bucket taken whole: the low bits are free
-      }
-    }
-    __syncthreads();
-    hi = shift;
-    if (s_done[0] && s_done[1]) break;
-  }
-  t_a = s_prefix[0];
-  t_b = s_prefix[1];
-  __syncthreads();
-}
-
-// Suffix scan over a TOPK_BINS histogram: the bin that holds the need-th largest element (1-based).
-// out[0] = bin, out[1] = rank of that element inside the bin, out[2] = size of the bin.  Block-wide; ends with a barrier.
-__device__ __forceinline__ void find_bucket(const unsigned* hh, int need, int* warp_tot, int* out) {
-  const int tid = threadIdx.x;
-  const int c0 = (int)hh[TOPK_BINS - 1 - 2 * tid], c1 = (int)hh[TOPK_BINS - 2 - 2 * tid];
-  const int incl = block_inclusive_scan(c0 + c1, warp_tot);
-  const int excl = incl - c0 - c1;
-  if (excl < need && excl + c0 >= need) { out[0] = TOPK_BINS - 1 - 2 * tid; out[1] = need - excl; out[2] = c0; }
-  else if (excl + c0 < need && incl >= need) { out[0] = TOPK_BINS - 2 - 2 * tid; out[1] = need - excl - c0; out[2] = c1; }
-  __syncthreads();
-}
-
-// Exact selection inside ONE top-digit bucket whose keys sit in shared memory (`st`, n_st keys, all with the same top
-// TOPK_BITS bits = prefix >> 53): the key T with exactly `need` bucket keys >= T.  11-bit passes over the stash only --
-// no global sweep; one or two passes for float scores.
-__device__ unsigned long long select_in_stash(const unsigned long long* st, int n_st, unsigned long long prefix, int need,
-                                              unsigned* hist, int* warp_tot, int* s_out) {
-  int hi = 64 - TOPK_BITS;
-  while (true) {
-    const int bits = hi < TOPK_BITS ? hi : TOPK_BITS, shift = hi - bits;
-    for (int i = threadIdx.x; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = 0u;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_st; i += TOPK_THREADS) {
-      const unsigned long long key = st[i];
-      if ((key >> hi) == (prefix >> hi)) atomicAdd(&hist[(unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u))], 1u);
-    }
-    __syncthreads();
-    find_bucket(hist, need, warp_tot, s_out);
+    hist_lookup2<THREADS, false>(hist, need, true, 0, false, warp_tot, phase, s_out);
     const int d = s_out[0], rest = s_out[1], cnt = s_out[2];
+    __syncthreads();
     prefix |= (unsigned long long)d << shift;
     need = rest;
     hi = shift;
     if (shift == 0 || cnt == rest) break;            // bucket taken whole: the low bits are free
   }
-  __syncthreads();
   return prefix;
 }
 
-constexpr int TOPK_STASH = 6144;                     // boundary-bucket keys a CTA can resolve in shared memory (48 KB)
-
-// `splits` CTAs per image.  CTA r produces ranks [r*k/splits, (r+1)*k/splits) of the descending top-k
-// order on its own: it selects the two splitters that bound its slice (exact radix select over all
-// keys of the image, L2-resident), compacts the keys between them into shared memory and sorts them
-// with a bitonic network that keeps E keys per thread in registers: strides < E are register swaps,
-// strides < 32E warp shuffles, only strides >= 32E go through shared memory.  The slices need no
-// merge and no inter-CTA communication, and the n log^2 n sort work shrinks with the slice.
+// shared-memory slot of logical element e: one pad entry per E elements keeps the blocked register <-> shared
+// transfers (thread t owns e = t*E .. t*E+E-1) at the 2-way minimum of 64-bit accesses
 template <int E>
-__global__ void __launch_bounds__(TOPK_THREADS, 1)
-topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __restrict__ boxes_all,
-            const float* __restrict__ cls_all, const int* __restrict__ valid_count, int n, int k, int splits,
-            BoxI16* __restrict__ out_boxes, float* __restrict__ out_scores, int* __restrict__ out_index,
-            int* __restrict__ out_count) {
-  constexpr int M = TOPK_THREADS * E;                 // sort size (power of two), >= slice length
-  extern __shared__ __align__(16) unsigned long long sbuf[];      // pad_slot<E>(M) entries
-  __shared__ unsigned hist[2 * TOPK_BINS];
-  __shared__ int warp_tot[TOPK_WARPS];
-  __shared__ unsigned long long s_prefix[2];
-  __shared__ int s_need[2], s_done[2], s_count, s_sel[4], s_stash[2];
+__device__ __forceinline__ int pad_slot(int e) { return E == 1 ? e : e + e / E; }
 
+template <int THREADS>
+__device__ __forceinline__ void sort_barrier() {
+  if (THREADS == SORT_T) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"n"(SORT_T) : "memory");
+}
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// Bitonic sort, descending, of M = SORT_T * E keys held E per thread (thread t owns elements t*E .. t*E+E-1) by the first
+// SORT_T threads of the CTA.  The network is unrolled at compile time: strides < E are register compare-exchanges,
+// strides < 32E one shuffle per key, larger strides one shared-memory exchange per key (two buffers alternate, so a
+// stage costs one barrier).  Per key and stage: fetch the partner, one 64-bit compare, one predicate, two selects.
+template <int THREADS, int E>
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long (&v)[E], unsigned long long* buf0,
+                                                  unsigned long long* buf1, int tid) {
+  constexpr int M = SORT_T * E;
+  int which = 0;
+#pragma unroll
+  for (int size = 2; size <= M; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= E) {
+        // partner element lives in thread tid ^ (stride / E), same register index
+        const bool keep_max = (((tid * E) & stride) == 0) == (((tid * E) & size) == 0);
+        unsigned long long other[E];
+        if (stride / E < 32) {
+#pragma unroll
+          for (int i = 0; i < E; ++i) other[i] = __shfl_xor_sync(0xffffffffu, v[i], stride / E);
+        } else {
+          unsigned long long* buf = which ? buf1 : buf0;
+          which ^= 1;
+#pragma unroll
+          for (int i = 0; i < E; ++i) buf[pad_slot<E>(tid * E + i)] = v[i];
+          sort_barrier<THREADS>();
+#pragma unroll
+          for (int i = 0; i < E; ++i) other[i] = buf[pad_slot<E>((tid ^ (stride / E)) * E + i)];
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+          const bool take = (v[i] < other[i]) == keep_max;
+          v[i] = take ? other[i] : v[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+          if ((i & stride) == 0) {
+            const bool desc = size < E ? ((i & size) == 0) : (((tid * E) & size) == 0);
+            const unsigned long long a = v[i], b = v[i | stride];
+            const bool swap = (a < b) == desc;
+            v[i] = swap ? b : a;
+            v[i | stride] = swap ? a : b;
+          }
+        }
+      }
+    }
+  }
+}
+
+struct ProposalArgs {
+  const float* regr;
+  const float* cls;
+  int rows, cols, n, k, splits, w_cap;
+  FastDiv div_a, div_cols;
+  unsigned long long* keys;                          // workspace [batch][n]
+  BoxI16* boxes;                                     // workspace [batch][n]
+  float4* dense;                                     // optional output
+  BoxI16* out_boxes;
+  float* out_scores;
+  int* out_index;
+  int* out_count;
+};
+
+// first / last value of the keys' high words that fall into bucket d (valid keys have a non-zero high word)
+__device__ __forceinline__ unsigned bucket_first(int d) { return d <= 0 ? 1u : (unsigned)(d + FINE_BASE) << (FINE_SHIFT - 32); }
+__device__ __forceinline__ unsigned bucket_last(int d) {
+  return d >= TOPK_BINS - 1 ? 0xffffffffu : ((unsigned)(d + FINE_BASE + 1) << (FINE_SHIFT - 32)) - 1u;
+}
+
+template <int THREADS, int E>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 4)
+proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
+  constexpr int M = SORT_T * E;                      // sort size (power of two), >= slice length
+  extern __shared__ __align__(16) unsigned long long sbuf[];      // M + SORT_T sort entries, then the candidate buffer
+  __shared__ unsigned hist_own[TOPK_BINS];           // this CTA's share of the bucket histogram; later the select passes'
+  __shared__ unsigned hist[TOPK_BINS];               // bucket histogram of the whole image
+  __shared__ unsigned warp_tot[2][32];
+  __shared__ int s_count, s_sel[6], s_total;
+  __shared__ short s_aw[FRCNN_MAX_ANCHORS], s_ah[FRCNN_MAX_ANCHORS];
+
+  const int splits = p.splits, n = p.n, k = p.k;
   const int img = blockIdx.x / splits, part = blockIdx.x - img * splits;
-  const unsigned long long* keys = keys_all + (size_t)img * n;
   const int tid = threadIdx.x, lane = tid & 31;
+  unsigned long long* keys = p.keys + (size_t)img * n;
+  BoxI16* boxes = p.boxes + (size_t)img * n;
+  cg::cluster_group cluster = cg::this_cluster();
+  int phase = 0;
 
+  for (int i = tid; i < TOPK_BINS; i += THREADS) hist_own[i] = 0u;
+  if (tid < tab.n) { s_aw[tid] = (short)tab.w[tid]; s_ah[tid] = (short)tab.h[tid]; }
   if (tid == 0) s_count = 0;
   __syncthreads();
-  const int* meta = valid_count + (size_t)img * TOPK_META;
-  const int n_valid = __ldg(meta);                    // counted by decode_kernel
-  const int m = min(k, n_valid);
-  const int first = (int)((long long)part * k / splits);                       // ranks [first, last) belong to this CTA
-  const int slice_end = (int)((long long)(part + 1) * k / splits);
-  const int last = min(slice_end, m);
 
+  // ---- 1. decode this CTA's share of the anchors ----
+  {
+    const int chunk = (n + splits - 1) / splits;
+    const int lo = part * chunk, hi = min(n, lo + chunk);
+    const float colmax = (float)(p.cols - 1), rowmax = (float)(p.rows - 1);
+    for (int i = lo + tid; i < hi; i += THREADS) {
+      const size_t g = (size_t)img * n + i;
+      const float4 r = ldg_f4(p.regr + 4 * g);
+      const float score = __ldg(p.cls + g);
+      const unsigned loc = fast_div((unsigned)i, p.div_a);
+      const int a = i - (int)loc * tab.n;
+      const unsigned cy_i = fast_div(loc, p.div_cols);
+      const int cx_i = (int)loc - (int)cy_i * p.cols;
+      const int aw = s_aw[a], ah = s_ah[a];
+
+      // anchors are integer valued -> exact in float32
+      float x = (float)(cx_i - (aw >> 1));
+      float y = (float)((int)cy_i - (ah >> 1));
+      float w = (float)aw;     // (x + aw) - x
+      float hgt = (float)ah;
+
+      // deltas / [10, 10, 5, 5] (util.py:118-121): one range guard for the four, the generic division outside it
+      float tx = div_const_core<10>(r.x), ty = div_const_core<10>(r.y);
+      float tw = div_const_core<5>(r.z), th = div_const_core<5>(r.w);
+      {
+        const float ax = fabsf(r.x), ay = fabsf(r.y), az = fabsf(r.z), aw4 = fabsf(r.w);
+        const float mn = fminf(fminf(ax, ay), fminf(az, aw4)), mx = fmaxf(fmaxf(ax, ay), fmaxf(az, aw4));
+        if (!(mn > 1e-30f && mx < 1e30f)) {
+          tx = __fdiv_rn(r.x, 10.0f); ty = __fdiv_rn(r.y, 10.0f);
+          tw = __fdiv_rn(r.z, 5.0f); th = __fdiv_rn(r.w, 5.0f);
+        }
+      }
+
+      x = __fadd_rn(x, __fmul_rn(w, 0.5f));          // w / 2.0: exact either way
+      y = __fadd_rn(y, __fmul_rn(hgt, 0.5f));
+      x = __fadd_rn(x, __fmul_rn(tx, w));
+      y = __fadd_rn(y, __fmul_rn(ty, hgt));
+      w = __fmul_rn(w, np_expf_inline(tw));
+      hgt = __fmul_rn(hgt, np_expf_inline(th));
+      x = __fsub_rn(x, __fmul_rn(w, 0.5f));
+      y = __fsub_rn(y, __fmul_rn(hgt, 0.5f));
+      x = rintf(x); y = rintf(y); w = rintf(w); hgt = rintf(hgt);     // np.round: half to even
+      float x2 = __fadd_rn(w, x), y2 = __fadd_rn(hgt, y);
+
+      x2 = max_nan(__fadd_rn(x, 1.0f), x2);
+      y2 = max_nan(__fadd_rn(y, 1.0f), y2);
+      x = max_nan(0.0f, x);
+      y = max_nan(0.0f, y);
+      x2 = min_nan(colmax, x2);
+      y2 = min_nan(rowmax, y2);
+
+      if (p.dense) p.dense[g] = make_float4(x, y, x2, y2);
+
+      const bool valid = (x2 > x) && (y2 > y);
+      unsigned long long key = 0ull;
+      BoxI16 b = {0, 0, 0, 0};
+      if (valid) {
+        // the high word of a valid key is never 0 (the one score pattern that maps there, a NaN, shares its neighbour's key
+        // value): the sweep tests validity and bucket membership on the high word alone
+        key = ((unsigned long long)max(mono_key(score), 1u) << 32) | (unsigned)i;
+        b.x1 = (short)(int)x; b.y1 = (short)(int)y; b.x2 = (short)(int)x2; b.y2 = (short)(int)y2;
+        atomicAdd(&hist_own[fine_digit(key)], 1u);
+      }
+      keys[i] = key;
+      boxes[i] = b;
+    }
+  }
+
+  // ---- 2. bucket histogram of the whole image: reduce-scatter + all-gather through distributed shared memory ----
+  if (splits > 1) {
+    const int bpr = (TOPK_BINS + splits - 1) / splits;                 // bins summed by one CTA
+    cluster.sync();                                  // also publishes the keys and boxes to the other CTAs of the image
+    const int b_lo = part * bpr, b_hi = min(TOPK_BINS, b_lo + bpr);
+    for (int b = b_lo + tid; b < b_hi; b += THREADS) {
+      unsigned sum = 0u;
+      for (int r = 0; r < splits; ++r) sum += cluster.map_shared_rank(hist_own, r)[b];
+      hist[b] = sum;
+    }
+    cluster.sync();
+    for (int b = tid; b < TOPK_BINS; b += THREADS) {
+      const int owner = b / bpr;
+      if (owner != part) hist[b] = cluster.map_shared_rank(hist, owner)[b];
+    }
+    cluster_arrive();                                // the matching wait is the last thing the CTA does: peers may
+                                                     // still be reading this CTA's `hist`, which is read-only from here on
+  } else {
+    __syncthreads();
+    for (int b = tid; b < TOPK_BINS; b += THREADS) hist[b] = hist_own[b];
+  }
+  __syncthreads();
+  bool cluster_pending = splits > 1;
+
+  // ---- 3. the slice: ranks [first, last) of the descending order ----
+  const int first = (int)((long long)part * k / splits);
+  const int slice_end = (int)((long long)(part + 1) * k / splits);
+  // one scan serves both bounds; the look-ups need n_valid (= the scan's total), so they run on saved registers
+  int da = TOPK_BINS, rest_a = 0, cnt_a = 0, db = -1, rest_b = 0, cnt_b = 0;
+  int n_valid, m, last;
+  {
+    constexpr int BPT = TOPK_BINS / THREADS;
+    unsigned c[BPT], sum = 0u;
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) { c[j] = hist[TOPK_BINS - 1 - BPT * tid - j]; sum += c[j]; }
+    const int incl = (int)block_inclusive_scan<THREADS>(sum, warp_tot, phase);
+    const int excl = incl - (int)sum;
+    if (tid == THREADS - 1) s_total = incl;
+    __syncthreads();
+    n_valid = s_total;
+    m = min(k, n_valid);
+    last = min(slice_end, m);
+    if (first < last) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int need = s ? last : first;
+        if (s ? (last >= n_valid) : (first <= 0)) continue;
+        if (excl < need && need <= incl) {
+          int e = excl;
+#pragma unroll
+          for (int j = 0; j < BPT; ++j) {
+            const int cj = (int)c[j];
+            if (need > e && need <= e + cj) { s_sel[3 * s] = TOPK_BINS - 1 - BPT * tid - j; s_sel[3 * s + 1] = need - e; s_sel[3 * s + 2] = cj; }
+            e += cj;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  unsigned long long* cand = sbuf + (M + SORT_T);    // candidate buffer: the slice plus the keys of its boundary buckets
+  unsigned* hist_sel = hist_own;                     // every peer finished reading hist_own before the second cluster barrier
   unsigned long long t_hi = ~0ull, t_lo = 1ull;
-  // Slice membership.  decode_kernel histogrammed the keys' top 11 bits; the buckets of the two slice bounds follow from
-  // that histogram alone.  ONE sweep over the image's keys then sends every key strictly between the two boundary
-  // buckets straight into the slice and parks the keys OF the boundary buckets in a shared-memory stash; the exact
-  // splitters are resolved inside the stash (select_in_stash) and the stash keys on the right side of them join the slice.
-  // The first version swept the keys three times (two select passes + compaction), each sweep an L2 round trip chain;
-  // it remains as the fall-back when the boundary buckets outgrow the stash (scores crowded into one quarter-octave).
-  unsigned long long* stash = sbuf + (M + TOPK_THREADS);
   bool done = first >= last;
+  int n_cand = 0;
   if (!done) {
     const bool need_hi = first > 0, need_lo = last < n_valid;
-    for (int i = tid; i < TOPK_BINS; i += TOPK_THREADS) hist[i] = (unsigned)__ldg(meta + 1 + i);
-    __syncthreads();
-    int da = TOPK_BINS, rest_a = 0, cnt_a = 0, db = -1, rest_b = 0, cnt_b = 0;
-    if (need_hi) {
-      find_bucket(hist, first, warp_tot, s_sel);
-      da = s_sel[0]; rest_a = s_sel[1]; cnt_a = s_sel[2];
-      __syncthreads();
-    }
-    if (need_lo) {
-      find_bucket(hist, last, warp_tot, s_sel);
-      db = s_sel[0]; rest_b = s_sel[1]; cnt_b = s_sel[2];
-      __syncthreads();
-    }
+    if (need_hi) { da = s_sel[0]; rest_a = s_sel[1]; cnt_a = s_sel[2]; }
+    if (need_lo) { db = s_sel[3]; rest_b = s_sel[4]; cnt_b = s_sel[5]; }
     const bool one_bucket = da == db;
-    const int n_stash_a = cnt_a, n_stash_b = one_bucket ? 0 : cnt_b;
-    if (n_stash_a + n_stash_b <= TOPK_STASH) {
+    bool sel_a = need_hi && rest_a != cnt_a;         // rest == cnt: the bucket goes to one side whole, nothing to select
+    bool sel_b = need_lo && rest_b != cnt_b;
+    // candidates = every key of the buckets [d_first .. d_last]: the boundary buckets that need a select, and everything
+    // between the two bounds; a boundary bucket that lies on the far side whole is left out
+    const int d_last = (sel_a || (one_bucket && sel_b)) ? da : da - 1;
+    const int d_first = need_lo ? ((sel_b || one_bucket || rest_b == cnt_b) ? db : db + 1) : 0;
+    const int extra_a = (d_last == da && need_hi) ? rest_a : 0;                          // candidates above the slice
+    const int extra_b = (need_lo && d_first == db && !(rest_b == cnt_b)) ? cnt_b - rest_b : 0;   // ... and below it
+    n_cand = (last - first) + extra_a + extra_b;
+    const bool clamped = (sel_a && (da == 0 || da == TOPK_BINS - 1)) || (sel_b && (db == 0 || db == TOPK_BINS - 1));
+    if (need_hi) t_hi = fine_prefix(da);
+    if (need_lo) t_lo = fine_prefix(db);
+    if (!clamped && n_cand <= p.w_cap && d_first <= d_last) {
       done = true;
-      if (tid == 0) { s_stash[0] = 0; s_stash[1] = 0; }
-      __syncthreads();
-      for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
-        unsigned long long kk[TOPK_U];
+      const unsigned h_lo = bucket_first(d_first), h_span = bucket_last(d_last) - h_lo;
+      // One sweep over the image's keys.  A thread counts the candidates among its TOPK_U keys, a warp scan and one
+      // shared atomic per warp place them.  Two register batches alternate, so the next batch's L2 reads are in flight
+      // while this one is placed.
+      const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
+      const unsigned count_s = (unsigned)__cvta_generic_to_shared(&s_count);
+      const unsigned long long* kp = keys + tid;
+      constexpr int BATCH = THREADS * TOPK_U;
+      auto load_batch = [&](unsigned long long (&dst)[TOPK_U], int base) {
+        if (base + BATCH <= n) {
+#pragma unroll
+          for (int u = 0; u < TOPK_U; ++u) dst[u] = __ldcg(kp + base + u * THREADS);
+        } else {
+#pragma unroll
+          for (int u = 0; u < TOPK_U; ++u) dst[u] = (base + u * THREADS + tid < n) ? __ldcg(kp + base + u * THREADS) : 0ull;
+        }
+      };
+      auto place_batch = [&](const unsigned long long (&src)[TOPK_U]) {
+        unsigned t[TOPK_U];
+        int mine = 0;
 #pragma unroll
         for (int u = 0; u < TOPK_U; ++u) {
-          const int i = base + u * TOPK_THREADS + tid;
-          kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
+          t[u] = (unsigned)(src[u] >> 32) - h_lo;    // a zero high word (no key) is below every range: h_lo >= 1
+          mine += t[u] <= h_span ? 1 : 0;
         }
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        int wbase = 0;
+        if (lane == 31 && incl) wbase = atom_shared_add(count_s, incl);
+        unsigned addr = cand_s + 8u * (unsigned)(__shfl_sync(0xffffffffu, wbase, 31) + incl - mine);
 #pragma unroll
         for (int u = 0; u < TOPK_U; ++u) {
-          const int dg = (int)(kk[u] >> (64 - TOPK_BITS));
-          const bool valid = kk[u] != 0ull;
-          const bool take = valid && dg < da && dg > db;
-          const unsigned ballot = __ballot_sync(0xffffffffu, take);
-          int wbase = 0;
-          if (lane == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
-          wbase = __shfl_sync(0xffffffffu, wbase, 0);
-          if (take) sbuf[pad_slot<E>(wbase + __popc(ballot & ((1u << lane) - 1u)))] = kk[u];
-          if (valid && dg == da) stash[atomicAdd(&s_stash[0], 1)] = kk[u];
-          else if (valid && dg == db) stash[n_stash_a + atomicAdd(&s_stash[1], 1)] = kk[u];
+          if (t[u] <= h_span) { st_shared_u64(addr, src[u]); addr += 8u; }
         }
+      };
+      unsigned long long ka[TOPK_U], kb[TOPK_U];
+      load_batch(ka, 0);
+      for (int base = 0; base < n; base += 2 * BATCH) {
+        load_batch(kb, base + BATCH);
+        place_batch(ka);
+        if (base + BATCH >= n) break;
+        load_batch(ka, base + 2 * BATCH);
+        place_batch(kb);
       }
       __syncthreads();
-      if (need_hi) t_hi = select_in_stash(stash, n_stash_a, (unsigned long long)da << (64 - TOPK_BITS), rest_a, hist, warp_tot, s_sel);
-      if (need_lo) t_lo = one_bucket ? select_in_stash(stash, n_stash_a, (unsigned long long)db << (64 - TOPK_BITS), rest_b, hist, warp_tot, s_sel)
-                                     : select_in_stash(stash + n_stash_a, n_stash_b, (unsigned long long)db << (64 - TOPK_BITS), rest_b, hist, warp_tot, s_sel);
-      for (int i = tid; i < n_stash_a + n_stash_b; i += TOPK_THREADS) {
-        const unsigned long long key = stash[i];
-        if (key >= t_lo && (first == 0 || key < t_hi)) sbuf[pad_slot<E>(atomicAdd(&s_count, 1))] = key;
+      // both exact splitters in one set of passes over the candidates: select A counts in the low half of the
+      // histogram words, select B in the high half
+      unsigned long long pa = t_hi, pb = t_lo;
+      int need_a = rest_a, need_b = rest_b;
+      for (int hi = FINE_SHIFT; (sel_a || sel_b) && hi > 0;) {
+        const int bits = hi < TOPK_BITS ? hi : TOPK_BITS, shift = hi - bits;
+        for (int i = tid; i < TOPK_BINS; i += THREADS) hist_sel[i] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n_cand; i += THREADS) {
+          const unsigned long long key = cand[i];
+          unsigned add = 0u;
+          if (sel_a && (key >> hi) == (pa >> hi)) add = 1u;
+          if (sel_b && (key >> hi) == (pb >> hi)) add += 0x10000u;
+          if (add) atomicAdd(&hist_sel[(unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u))], add);
+        }
+        __syncthreads();
+        hist_lookup2<THREADS, true>(hist_sel, need_a, sel_a, need_b, sel_b, warp_tot, phase, s_sel);
+        if (sel_a) {
+          pa |= (unsigned long long)s_sel[0] << shift;
+          need_a = s_sel[1];
+          if (shift == 0 || s_sel[2] == need_a) sel_a = false;         // bucket taken whole: the low bits are free
+        }
+        if (sel_b) {
+          pb |= (unsigned long long)s_sel[3] << shift;
+          need_b = s_sel[4];
+          if (shift == 0 || s_sel[5] == need_b) sel_b = false;
+        }
+        hi = shift;
+        __syncthreads();
       }
+      t_hi = pa;
+      t_lo = pb;
     }
   }
   if (!done) {
     // fall-back: exact splitters by radix select over all keys (keys >= t_lo and < t_hi are exactly the ranks [first, last))
+    if (cluster_pending) { cluster_wait(); cluster_pending = false; }   // `hist` is about to be reused
     const bool need_hi = first > 0, need_lo = last < n_valid;
-    unsigned long long ta = 0ull, tb = 0ull;
-    if (need_hi && need_lo) {
-      radix_select2(keys, meta + 1, n, first, last, true, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
-      t_hi = ta;
-      t_lo = tb;
-    } else if (need_hi) {
-      radix_select2(keys, meta + 1, n, first, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
-      t_hi = ta;
-    } else if (need_lo) {
-      radix_select2(keys, meta + 1, n, last, 0, false, hist, warp_tot, s_prefix, s_need, s_done, ta, tb);
-      t_lo = ta;
-    }
-    // compaction of the slice into shared memory (order irrelevant, sorted next)
-    for (int base = 0; base < n; base += TOPK_THREADS * TOPK_U) {
+    t_hi = ~0ull;
+    t_lo = 1ull;
+    if (need_hi) t_hi = radix_select_global<THREADS>(keys, n, first, hist, warp_tot, phase, s_sel);
+    if (need_lo) t_lo = radix_select_global<THREADS>(keys, n, last, hist, warp_tot, phase, s_sel);
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += THREADS * TOPK_U) {
       unsigned long long kk[TOPK_U];
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
-        const int i = base + u * TOPK_THREADS + tid;
-        kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
+        const int i = base + u * THREADS + tid;
+        kk[u] = (i < n) ? __ldcg(keys + i) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
@@ -364,132 +570,178 @@ topk_kernel(const unsigned long long* __restrict__ keys_all, const BoxI16* __res
         int wbase = 0;
         if (lane == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (take) sbuf[pad_slot<E>(wbase + __popc(ballot & ((1u << lane) - 1u)))] = kk[u];
+        if (take) cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = kk[u];
       }
     }
+    __syncthreads();
+    n_cand = first < last ? last - first : 0;
+  }
+
+  // The candidates that are not of the slice (boundary-bucket keys beyond the splitters) become zeros, the smallest
+  // key: they sink behind the slice.  More than M candidates (only when the boundary buckets are large) are compacted
+  // through the sort buffer first.
+  const bool in_first = first == 0;
+  if (n_cand > M) {
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_cand; i0 += THREADS) {
+      const int i = i0 + tid;
+      const unsigned long long key = i < n_cand ? cand[i] : 0ull;
+      const bool take = key != 0ull && key >= t_lo && (in_first || key < t_hi);
+      const unsigned ballot = __ballot_sync(0xffffffffu, take);
+      int wbase = 0;
+      if (lane == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (take) sbuf[wbase + __popc(ballot & ((1u << lane) - 1u))] = key;
+    }
+    __syncthreads();
+    n_cand = s_count;                                // = last - first
+    for (int i = tid; i < n_cand; i += THREADS) cand[i] = sbuf[i];
   }
   __syncthreads();
-  for (int i = s_count + tid; i < M; i += TOPK_THREADS) sbuf[pad_slot<E>(i)] = 0ull;   // pad with the smallest key
-  __syncthreads();
 
-  // ---- bitonic sort, descending, E keys per thread in registers ----
-  unsigned long long v[E];
+  // ---- 4. sort on the first SORT_T threads ----
+  if (tid < SORT_T) {
+    unsigned long long v[E];
 #pragma unroll
-  for (int i = 0; i < E; ++i) v[i] = sbuf[pad_slot<E>(tid * E + i)];
-  for (int size = 2; size <= M; size <<= 1) {
-    int stride = size >> 1;
-    if (stride >= 32 * E) {
-      // cross-warp strides of this merge level: classic shared-memory passes
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < E; ++i) sbuf[pad_slot<E>(tid * E + i)] = v[i];
-      for (; stride >= 32 * E; stride >>= 1) {
-        __syncthreads();
-        for (int t = tid; t < (M >> 1); t += TOPK_THREADS) {
-          const int lo = 2 * t - (t & (stride - 1)), hi2 = lo + stride;
-          const bool desc = ((lo & size) == 0);
-          const unsigned long long a = sbuf[pad_slot<E>(lo)], b = sbuf[pad_slot<E>(hi2)];
-          if ((a < b) == desc) { sbuf[pad_slot<E>(lo)] = b; sbuf[pad_slot<E>(hi2)] = a; }
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < E; ++i) v[i] = sbuf[pad_slot<E>(tid * E + i)];
+    for (int i = 0; i < E; ++i) {
+      const int j = i * SORT_T + tid;                // any assignment of candidates to sort elements will do
+      const unsigned long long key = j < n_cand ? cand[j] : 0ull;
+      v[i] = (key >= t_lo && (in_first || key < t_hi)) ? key : 0ull;
     }
-    for (; stride >= E; stride >>= 1) {              // partner in another lane of the warp
-      const int lane_xor = stride / E;
+    bitonic_sort_regs<THREADS, E>(v, sbuf, cand, tid);
+    sort_barrier<THREADS>();                         // the last exchange may still be read from sbuf
 #pragma unroll
-      for (int i = 0; i < E; ++i) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[i], lane_xor);
-        const int e = tid * E + i;
-        const bool want_max = ((e & stride) == 0) == ((e & size) == 0);
-        v[i] = want_max ? (v[i] > other ? v[i] : other) : (v[i] < other ? v[i] : other);
-      }
-    }
-#pragma unroll
-    for (int st = E >> 1; st > 0; st >>= 1) {        // partner in the same thread
-      if (st <= stride) {
-#pragma unroll
-        for (int i = 0; i < E; ++i) {
-          if ((i & st) == 0) {
-            const int e = tid * E + i;
-            const bool desc = ((e & size) == 0);
-            const unsigned long long a = v[i], b = v[i | st];
-            if ((a < b) == desc) { v[i] = b; v[i | st] = a; }
-          }
-        }
-      }
-    }
+    for (int i = 0; i < E; ++i) sbuf[pad_slot<E>(tid * E + i)] = v[i];
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < E; ++i) sbuf[pad_slot<E>(tid * E + i)] = v[i];
-  __syncthreads();
 
-  const BoxI16* boxes = boxes_all + (size_t)img * n;
-  const float* cls = cls_all + (size_t)img * n;
-  for (int r = first + tid; r < slice_end; r += TOPK_THREADS) {
+  // ---- 5. gather at the final ranks ----
+  const float* cls = p.cls + (size_t)img * n;
+  for (int r = first + tid; r < slice_end; r += THREADS) {
     const size_t o = (size_t)img * k + r;
     if (r < last) {
       const int idx = (int)(unsigned)(sbuf[pad_slot<E>(r - first)] & 0xffffffffull);
-      out_boxes[o] = boxes[idx];
-      out_scores[o] = __ldg(cls + idx);
-      out_index[o] = idx;
+      const uint2 bw = __ldcg(reinterpret_cast<const uint2*>(boxes + idx));   // written by a peer CTA: L2, not the read-only path
+      reinterpret_cast<uint2*>(p.out_boxes)[o] = bw;
+      p.out_scores[o] = __ldg(cls + idx);
+      p.out_index[o] = idx;
     } else {
-      out_boxes[o] = BoxI16{0, 0, 0, 0};
-      out_scores[o] = 0.0f;
-      out_index[o] = -1;
+      p.out_boxes[o] = BoxI16{0, 0, 0, 0};
+      p.out_scores[o] = 0.0f;
+      p.out_index[o] = -1;
     }
   }
-  if (tid == 0 && part == 0) out_count[img] = m;
+  if (tid == 0 && part == 0) p.out_count[img] = m;
+  if (cluster_pending) cluster_wait();               // no CTA may exit while a peer can still read its shared memory
 }
 
-template <int E>
-static int launch_topk(frcnn_handle* h, cudaStream_t stream, const unsigned long long* keys, const BoxI16* boxes,
-                       const float* cls, const int* valid_count, int n, int k, int splits, int batch, BoxI16* out_boxes,
-                       float* out_scores, int32_t* out_index, int32_t* out_count) {
-  const size_t smem = (size_t)(TOPK_THREADS * E + TOPK_THREADS + TOPK_STASH) * sizeof(unsigned long long);
-  if (smem + 12 * 1024 > (size_t)h->max_smem_optin)
-    return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k too large for the shared-memory sort%s%s");
-  FRCNN_CUDA(h, cudaFuncSetAttribute(topk_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_kernel<E><<<batch * splits, TOPK_THREADS, smem, stream>>>(keys, boxes, cls, valid_count, n, k, splits, out_boxes,
-                                                               out_scores, out_index, out_count);
-  FRCNN_LAUNCH_CHECK(h, "topk_kernel");
+template <int THREADS, int E>
+static int launch_proposals(frcnn_handle* h, cudaStream_t stream, const ProposalArgs& args, const AnchorTable& tab,
+                            int batch, bool probe_only) {
+  const size_t smem = (size_t)(SORT_T * E + SORT_T + args.w_cap) * sizeof(unsigned long long);
+  auto kernel = proposals_kernel<THREADS, E>;
+  FRCNN_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (args.splits > 8) FRCNN_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(batch * args.splits));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)args.splits;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (probe_only) {
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+    return clusters > 0 ? FRCNN_OK : FRCNN_ERR_UNSUPPORTED;
+  }
+  FRCNN_CUDA(h, cudaLaunchKernelEx(&cfg, kernel, args, tab));
+  FRCNN_LAUNCH_CHECK(h, "proposals_kernel");
   return FRCNN_OK;
+}
+
+template <int THREADS>
+static int launch_proposals_e(frcnn_handle* h, cudaStream_t stream, const ProposalArgs& args, const AnchorTable& tab,
+                              int batch, int e, bool probe_only) {
+  switch (e) {
+    case 1: return launch_proposals<THREADS, 1>(h, stream, args, tab, batch, probe_only);
+    case 2: return launch_proposals<THREADS, 2>(h, stream, args, tab, batch, probe_only);
+    case 4: return launch_proposals<THREADS, 4>(h, stream, args, tab, batch, probe_only);
+    default: return launch_proposals<THREADS, 8>(h, stream, args, tab, batch, probe_only);
+  }
+}
+
+static int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : fallback;
 }
 
 int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, const float* cls,
                        const AnchorTable& tab, int rows, int cols, int k, int batch,
                        int16_t* out_boxes, float* out_scores, int32_t* out_index,
                        int32_t* out_count, float* dense_boxes) {
-  const int n = rows * cols * tab.n;
-  if (k > TOPK_THREADS * 16)
-    return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k above 16384 is not supported%s%s");
+  const long long n_ll = (long long)rows * cols * tab.n;
+  if (n_ll >= (1ll << 31)) return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: more than 2^31 anchors per image%s%s");
+  const int n = (int)n_ll;
+  if (k > MAX_SPLITS * SORT_T * 8)
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k above 32768 is not supported%s%s");
   const size_t key_bytes = align_up((size_t)batch * n * sizeof(unsigned long long), 256);
   const size_t box_bytes = align_up((size_t)batch * n * sizeof(BoxI16), 256);
   void* ws = nullptr;
-  int rc = arena_get(h, stream, key_bytes + box_bytes + (size_t)batch * TOPK_META * sizeof(int), &ws);
+  int rc = arena_get(h, stream, key_bytes + box_bytes, &ws);
   if (rc) return rc;
-  auto* keys = reinterpret_cast<unsigned long long*>(ws);
-  auto* boxes = reinterpret_cast<BoxI16*>(reinterpret_cast<char*>(ws) + key_bytes);
-  int* valid_count = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + key_bytes + box_bytes);
-  FRCNN_CUDA(h, cudaMemsetAsync(valid_count, 0, (size_t)batch * TOPK_META * sizeof(int), stream));
 
-  dim3 grid((n + 255) / 256, batch);
-  decode_kernel<<<grid, 256, 0, stream>>>(regr, cls, tab, rows, cols, n, keys, boxes,
-                                         reinterpret_cast<float4*>(dense_boxes), valid_count);
-  FRCNN_LAUNCH_CHECK(h, "decode_kernel");
-  // CTAs per image: as many rank slices as keep the GPU filled in one wave, slices of >= 896 keys (k = 8000 at batch 1:
-  // eight 1000-key slices sorted one key per thread; same-box A/B 38 -> 34 us on clustered scores, equal on uniform ones)
-  int splits = 1;
-  while (splits < 8 && (long long)batch * splits * 2 <= h->sm_count && k / (splits * 2) >= 896) splits <<= 1;
-  const int slice = (k + splits - 1) / splits + 1;
-  auto* ob = reinterpret_cast<BoxI16*>(out_boxes);
-  if (slice <= TOPK_THREADS * 1) return launch_topk<1>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
-  if (slice <= TOPK_THREADS * 2) return launch_topk<2>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
-  if (slice <= TOPK_THREADS * 4) return launch_topk<4>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
-  if (slice <= TOPK_THREADS * 8) return launch_topk<8>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
-  return launch_topk<16>(h, stream, keys, boxes, cls, valid_count, n, k, splits, batch, ob, out_scores, out_index, out_count);
+  ProposalArgs args;
+  args.regr = regr;
+  args.cls = cls;
+  args.rows = rows; args.cols = cols; args.n = n; args.k = k;
+  args.div_a = make_fastdiv((unsigned)tab.n);
+  args.div_cols = make_fastdiv((unsigned)cols);
+  args.keys = reinterpret_cast<unsigned long long*>(ws);
+  args.boxes = reinterpret_cast<BoxI16*>(reinterpret_cast<char*>(ws) + key_bytes);
+  args.dense = reinterpret_cast<float4*>(dense_boxes);
+  args.out_boxes = reinterpret_cast<BoxI16*>(out_boxes);
+  args.out_scores = out_scores;
+  args.out_index = out_index;
+  args.out_count = out_count;
+
+  // CTAs per image (= cluster size): slices of about 1000 ranks, sorted four keys per thread; a small k still gets
+  // enough CTAs to decode the anchors in parallel.  One CTA per SM with 1024 threads while the GPU has SMs to spare,
+  // 256-thread CTAs (four or more per SM) once batch * splits exceeds the SM count.
+  int splits = (k + 999) / 1000;
+  const int for_decode = (n + 4095) / 4096;
+  if (splits < for_decode) splits = for_decode < 8 ? for_decode : 8;
+  if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+  splits = env_int("FRCNN_TOPK_SPLITS", splits);      // experiment knobs (benchmarks/prop_one.py)
+  if (splits < 1) splits = 1;
+  if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+  bool wide = (long long)batch * splits <= h->sm_count;
+  const int force_threads = env_int("FRCNN_TOPK_THREADS", 0);
+  if (force_threads) wide = force_threads == 1024;
+  for (;; splits = (splits + 1) / 2) {
+    const int slice = (k + splits - 1) / splits;
+    int e = 1;
+    while (SORT_T * e < slice) e <<= 1;
+    if (e > 8) return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k too large for the shared-memory sort%s%s");
+    args.splits = splits;
+    // a cluster of sixteen 1024-thread CTAs may not fit one GPC: try the narrow CTAs before giving up slices
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      const bool w = attempt == 0 ? wide : false;
+      if (attempt == 1 && !wide) break;
+      args.w_cap = w ? 6144 : (e == 8 ? 3072 : 2560);   // >= M + SORT_T: the candidate buffer doubles as the sort's second exchange buffer
+      const int ok = w ? launch_proposals_e<1024>(h, stream, args, tab, batch, e, true)
+                       : launch_proposals_e<256>(h, stream, args, tab, batch, e, true);
+      if (ok == FRCNN_OK)
+        return w ? launch_proposals_e<1024>(h, stream, args, tab, batch, e, false)
+                 : launch_proposals_e<256>(h, stream, args, tab, batch, e, false);
+    }
+    if (splits == 1) return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: no cluster configuration fits this device%s%s");
+  }
 }
 
 }  // namespace frcnn

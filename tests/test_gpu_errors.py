@@ -27,7 +27,7 @@ def test_invalid_arguments_raise_with_message():
     assert e.value.code == _lib.ERR_UNSUPPORTED
     with pytest.raises(_lib.FrcnnError) as e:                          # top-k above the sort capacity
         ops.decode_topk(dev(np.zeros((1, 64, 64, 36), np.float32)), dev(np.zeros((1, 64, 64, 9), np.float32)),
-                        np.ones((9, 2), np.int64) * 64, 16, 20000)
+                        np.ones((9, 2), np.int64) * 64, 16, 36000)
     assert e.value.code == _lib.ERR_UNSUPPORTED
     with pytest.raises(_lib.FrcnnError):                               # MAX mode without an arg-max buffer
         ctx.call("frcnn_roi_fwd", 1, ptr(torch.zeros(16, device="cuda")), 2, 2, 4, ptr(torch.zeros(4, dtype=torch.int16, device="cuda")),

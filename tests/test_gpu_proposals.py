@@ -409,3 +409,64 @@ def test_one_handle_two_streams_share_scratch_safely(ops):
         torch.cuda.synchronize()
         for w, g in zip(want_a + want_b, list(got_a) + list(got_b)):
             assert torch.equal(w, g)
+
+
+def _score_family(name, n, rng):
+    """Objectness arrays that exercise every slice-membership path of proposals_kernel: the bucket window is
+    [2^-32, 1) with 64 buckets per octave, everything else lands in the two clamped end buckets."""
+    u = (rng.permutation(n).astype(np.float64) + 0.5) / n
+    if name == "logits":                       # negative and > 1: both clamped buckets, fall-back selects
+        return ((u - 0.5) * 30.0).astype(np.float32)
+    if name == "sigmoid_of_logits":            # a trained head: mass near 0 and a saturated top
+        return (1.0 / (1.0 + np.exp(-(u - 0.7) * 40.0))).astype(np.float32)
+    if name == "tiny":                         # everything below the window
+        return (u * 1e-12).astype(np.float32)
+    if name == "above_one":
+        return (1.0 + u * 5.0).astype(np.float32)
+    if name == "saturated_top":                # thousands of exact 1.0 (ties inside the clamped top bucket)
+        return np.minimum(u * 1.6, 1.0).astype(np.float32)
+    if name == "one_bucket":                   # all scores inside one 1/64-octave bucket: stash overflow -> fall-back
+        return (0.75 + u * 1e-3).astype(np.float32)
+    if name == "two_values":
+        return np.where(u < 0.5, 0.25, 0.5).astype(np.float32)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("family", ["logits", "sigmoid_of_logits", "tiny", "above_one", "saturated_top", "one_bucket",
+                                    "two_values"])
+@pytest.mark.parametrize("k", [8000, 12000, 700])
+def test_decode_topk_score_distributions(ops, family, k):
+    dims = O.anchor_table([128, 256, 512])
+    from faster_rcnn_b200 import synth
+    _, regr = synth.rpn_outputs(38, 63, 9, 300 + k, clustered=True)
+    rng = np.random.default_rng(k)
+    cls = _score_family(family, 38 * 63 * 9, rng).reshape(1, 38, 63, 9)
+    _check_decode_topk(ops, dims, cls, regr, k)
+
+
+def test_decode_topk_large_k(ops):
+    """k = 20000 of 36864 anchors: sixteen CTAs per image, 2048-key sorts."""
+    dims = O.anchor_table([128, 256, 512])
+    from faster_rcnn_b200 import synth
+    cls, regr = synth.rpn_outputs(64, 64, 9, 901, clustered=True)
+    _check_decode_topk(ops, dims, cls, regr, 20000)
+    _check_decode_topk(ops, dims, cls, regr, 32768)
+
+
+def test_decode_topk_batch_uses_narrow_ctas(ops):
+    """24 images x 8 slices exceeds the SM count: the 256-thread variant of the kernel, several CTAs per SM."""
+    dims = O.anchor_table([128, 256, 512])
+    from faster_rcnn_b200 import synth
+    b = 24
+    pairs = [synth.rpn_outputs(38, 63, 9, 700 + i, clustered=bool(i % 2)) for i in range(b)]
+    cls, regr = np.concatenate([p[0] for p in pairs]), np.concatenate([p[1] for p in pairs])
+    cls[3] = _score_family("logits", cls[3].size, np.random.default_rng(3)).reshape(cls[3].shape)
+    cls[4] = _score_family("one_bucket", cls[4].size, np.random.default_rng(4)).reshape(cls[4].shape)
+    boxes, scores, index, count, dense = ops.decode_topk(dev(regr), dev(cls), dims, 16, 8000, want_dense=True)
+    boxes, scores, index, count, dense = host(boxes), host(scores), host(index), host(count), host(dense)
+    for i in range(b):
+        wb, wp, widx = O.topk_proposals(dense[i].copy(), cls[i].reshape(-1), 8000)
+        n = int(count[i])
+        assert n == len(wb), i
+        assert np.array_equal(index[i, :n], widx) and np.array_equal(boxes[i, :n], wb) and np.array_equal(scores[i, :n], wp), i
+        assert np.all(index[i, n:] == -1)
