@@ -59,6 +59,32 @@ def timeit(fn, iters, warmup=5, min_ms=10.0):
     return a.elapsed_time(b) / iters
 
 
+def graph_timeit(fn, calls=20, replays=20):
+    """mean ms per call with `calls` back-to-back calls captured in one CUDA graph: the GPU time of a stage whose eager
+    call is bound by the host (ctypes + torch.empty + launch, about 30 us per call for the proposal stage)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(calls):
+            fn()
+    for _ in range(3):
+        g.replay()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(replays):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / (calls * replays)
+
+
 def rpn_batch(rows, cols, dims, batch, seed, clustered):
     pairs = [synth.rpn_outputs(rows, cols, len(dims), seed + i, clustered=clustered) for i in range(batch)]
     return dev(np.concatenate([p[0] for p in pairs])), dev(np.concatenate([p[1] for p in pairs]))
@@ -98,15 +124,18 @@ def main():
             n = rows * cols * len(dims)
             if want("decode"):
                 ms = timeit(lambda: ops.decode_topk(regr, cls, dims, 16, k), args.iters)
-                rec("decode_topk", "%s b%d" % (tag, batch), ms, batch, batch * (n * 20 + min(k, n) * 16))
+                rec("decode_topk", "%s b%d" % (tag, batch), ms, batch, batch * (n * 20 + min(k, n) * 16),
+                    graph_ms=round(graph_timeit(lambda: ops.decode_topk(regr, cls, dims, 16, k)), 5))
             tb, ts, _, tc = ops.decode_topk(regr, cls, dims, 16, k)
             if want("nms"):
                 ms = timeit(lambda: ops.nms_i16(tb, ts, tc, 0.7, post), args.iters)
                 kept = int(ops.nms_i16(tb, ts, tc, 0.7, post)[1].float().mean().item())
-                rec("nms_i16", "%s b%d" % (tag, batch), ms, batch, kept_mean=kept)
+                rec("nms_i16", "%s b%d" % (tag, batch), ms, batch, kept_mean=kept,
+                    graph_ms=round(graph_timeit(lambda: ops.nms_i16(tb, ts, tc, 0.7, post)), 5))
             if want("proposals"):
                 ms = timeit(lambda: ops.proposals(regr, cls, dims, 16, k, 0.7, post), args.iters)
-                rec("proposals_fused", "%s b%d" % (tag, batch), ms, batch)
+                rec("proposals_fused", "%s b%d" % (tag, batch), ms, batch,
+                    graph_ms=round(graph_timeit(lambda: ops.proposals(regr, cls, dims, 16, k, 0.7, post)), 5))
 
     # ---- RoI layer: C1 (320 RoIs) x 64 images, C5 (2000 RoIs, 1 image and 8 images), forward + backward, both modes --
     for tag, n_rois, batch in (("C1 320 rois", 320, 64), ("C5 2000 rois", 2000, 1), ("C5 2000 rois", 2000, 8)):

@@ -581,7 +581,9 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
   // key: they sink behind the slice.  More than M candidates (only when the boundary buckets are large) are compacted
   // through the sort buffer first.
   const bool in_first = first == 0;
+  const unsigned long long* src = cand;
   if (n_cand > M) {
+    src = sbuf;
     if (tid == 0) s_count = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n_cand; i0 += THREADS) {
@@ -596,8 +598,8 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
     }
     __syncthreads();
     n_cand = s_count;                                // = last - first
-    for (int i = tid; i < n_cand; i += THREADS) cand[i] = sbuf[i];
   }
+  const bool compacted = src == sbuf;
   __syncthreads();
 
   // ---- 4. sort on the first SORT_T threads ----
@@ -606,9 +608,10 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       const int j = i * SORT_T + tid;                // any assignment of candidates to sort elements will do
-      const unsigned long long key = j < n_cand ? cand[j] : 0ull;
+      const unsigned long long key = j < n_cand ? src[j] : 0ull;
       v[i] = (key >= t_lo && (in_first || key < t_hi)) ? key : 0ull;
     }
+    if (compacted) sort_barrier<THREADS>();      // the network's first exchange overwrites the buffer just read
     bitonic_sort_regs<THREADS, E>(v, sbuf, cand, tid);
     sort_barrier<THREADS>();                         // the last exchange may still be read from sbuf
 #pragma unroll
@@ -710,12 +713,14 @@ int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, 
   args.out_index = out_index;
   args.out_count = out_count;
 
-  // CTAs per image (= cluster size): slices of about 1000 ranks, sorted four keys per thread; a small k still gets
-  // enough CTAs to decode the anchors in parallel.  One CTA per SM with 1024 threads while the GPU has SMs to spare,
-  // 256-thread CTAs (four or more per SM) once batch * splits exceeds the SM count.
+  // CTAs per image (= cluster size): slices of at most 1000 ranks, sorted four keys per thread.  While the GPU has SMs to
+  // spare the image is spread over the largest cluster (decode, sweep and sort all shrink per CTA: 17.7 -> 14.1 us at
+  // one image, k = 8000); a small k still gets enough CTAs to decode the anchors in parallel.  One CTA per SM with 1024
+  // threads while batch * splits fits the SM count, 256-thread CTAs (four or more per SM) beyond.
   int splits = (k + 999) / 1000;
   const int for_decode = (n + 4095) / 4096;
   if (splits < for_decode) splits = for_decode < 8 ? for_decode : 8;
+  if ((long long)batch * MAX_SPLITS <= h->sm_count && n >= 4096) splits = MAX_SPLITS;
   if (splits > MAX_SPLITS) splits = MAX_SPLITS;
   splits = env_int("FRCNN_TOPK_SPLITS", splits);      // experiment knobs (benchmarks/prop_one.py)
   if (splits < 1) splits = 1;
