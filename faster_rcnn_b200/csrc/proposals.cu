@@ -166,10 +166,11 @@ __device__ __forceinline__ void hist_lookup2(const unsigned* hh, int need0, bool
   __syncthreads();
 }
 
-// Fall-back: exact selection over all keys of the image, the key T with exactly `need` valid keys >= T (keys are unique
-// and non-zero; 0 < need <= number of valid keys).  MSB-first radix select, one sweep per 11-bit digit.
+// Fall-back: exact selection over all keys of the image, the key T with exactly `need` valid keys >= T (a key is the
+// score word and, below it, the anchor's position; 0 < need <= number of valid keys).  MSB-first radix select, one sweep
+// per 11-bit digit.
 template <int THREADS>
-__device__ unsigned long long radix_select_global(const unsigned long long* keys, int n, int need, unsigned* hist,
+__device__ unsigned long long radix_select_global(const unsigned* skeys, int n, int need, unsigned* hist,
                                                   unsigned (*warp_tot)[32], int& phase, int* s_out) {
   unsigned long long prefix = 0ull;
   int hi = 64;
@@ -178,16 +179,16 @@ __device__ unsigned long long radix_select_global(const unsigned long long* keys
     for (int i = threadIdx.x; i < TOPK_BINS; i += THREADS) hist[i] = 0u;
     __syncthreads();
     for (int base = 0; base < n; base += THREADS * TOPK_U) {
-      unsigned long long kk[TOPK_U];
+      unsigned kk[TOPK_U];
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
         const int i = base + u * THREADS + (int)threadIdx.x;
-        kk[u] = (i < n) ? __ldcg(keys + i) : 0ull;
+        kk[u] = (i < n) ? __ldcg(skeys + i) : 0u;
       }
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
-        const unsigned long long key = kk[u];
-        if (key != 0ull && (hi == 64 || (key >> hi) == (prefix >> hi)))
+        const unsigned long long key = ((unsigned long long)kk[u] << 32) | (unsigned)(base + u * THREADS + (int)threadIdx.x);
+        if (kk[u] != 0u && (hi == 64 || (key >> hi) == (prefix >> hi)))
           atomicAdd(&hist[(unsigned)((key >> shift) & (unsigned long long)((1u << bits) - 1u))], 1u);
       }
     }
@@ -272,7 +273,9 @@ struct ProposalArgs {
   const float* cls;
   int rows, cols, n, k, splits, w_cap;
   FastDiv div_a, div_cols;
-  unsigned long long* keys;                          // workspace [batch][n]
+  unsigned* skeys;                                   // workspace [batch][n_pad]: order-preserving score words, 0 = no box;
+                                                     // a sort key is (score word << 32) | position
+  int n_pad;                                         // n rounded up to a multiple of 4 (128-bit loads)
   BoxI16* boxes;                                     // workspace [batch][n]
   float4* dense;                                     // optional output
   BoxI16* out_boxes;
@@ -301,7 +304,7 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
   const int splits = p.splits, n = p.n, k = p.k;
   const int img = blockIdx.x / splits, part = blockIdx.x - img * splits;
   const int tid = threadIdx.x, lane = tid & 31;
-  unsigned long long* keys = p.keys + (size_t)img * n;
+  unsigned* skeys = p.skeys + (size_t)img * p.n_pad;
   BoxI16* boxes = p.boxes + (size_t)img * n;
   cg::cluster_group cluster = cg::this_cluster();
   int phase = 0;
@@ -313,10 +316,11 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
 
   // ---- 1. decode this CTA's share of the anchors ----
   {
-    const int chunk = (n + splits - 1) / splits;
-    const int lo = part * chunk, hi = min(n, lo + chunk);
+    const int chunk = (p.n_pad + splits - 1) / splits;
+    const int lo = part * chunk, hi = min(p.n_pad, lo + chunk);
     const float colmax = (float)(p.cols - 1), rowmax = (float)(p.rows - 1);
     for (int i = lo + tid; i < hi; i += THREADS) {
+      if (i >= n) { skeys[i] = 0u; continue; }       // padding of the last 128-bit group
       const size_t g = (size_t)img * n + i;
       const float4 r = ldg_f4(p.regr + 4 * g);
       const float score = __ldg(p.cls + g);
@@ -365,16 +369,16 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
       if (p.dense) p.dense[g] = make_float4(x, y, x2, y2);
 
       const bool valid = (x2 > x) && (y2 > y);
-      unsigned long long key = 0ull;
+      unsigned skey = 0u;
       BoxI16 b = {0, 0, 0, 0};
       if (valid) {
-        // the high word of a valid key is never 0 (the one score pattern that maps there, a NaN, shares its neighbour's key
-        // value): the sweep tests validity and bucket membership on the high word alone
-        key = ((unsigned long long)max(mono_key(score), 1u) << 32) | (unsigned)i;
+        // the score word of a box is never 0 (the one score pattern that maps there, a NaN, shares its neighbour's word):
+        // the sweep tests validity and bucket membership on this word alone
+        skey = max(mono_key(score), 1u);
         b.x1 = (short)(int)x; b.y1 = (short)(int)y; b.x2 = (short)(int)x2; b.y2 = (short)(int)y2;
-        atomicAdd(&hist_own[fine_digit(key)], 1u);
+        atomicAdd(&hist_own[fine_digit((unsigned long long)skey << 32)], 1u);
       }
-      keys[i] = key;
+      skeys[i] = skey;
       boxes[i] = b;
     }
   }
@@ -469,24 +473,25 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
       // while this one is placed.
       const unsigned cand_s = (unsigned)__cvta_generic_to_shared(cand);
       const unsigned count_s = (unsigned)__cvta_generic_to_shared(&s_count);
-      const unsigned long long* kp = keys + tid;
-      constexpr int BATCH = THREADS * TOPK_U;
-      auto load_batch = [&](unsigned long long (&dst)[TOPK_U], int base) {
-        if (base + BATCH <= n) {
+      const uint4* kp = reinterpret_cast<const uint4*>(skeys) + tid;
+      const int n4 = p.n_pad >> 2;
+      constexpr int U4 = TOPK_U / 2;                 // 128-bit loads per thread and batch: 4 * U4 keys
+      constexpr int BATCH = THREADS * U4;            // in 128-bit groups
+      auto load_batch = [&](uint4 (&dst)[U4], int base) {
+        if (base + BATCH <= n4) {
 #pragma unroll
-          for (int u = 0; u < TOPK_U; ++u) dst[u] = __ldcg(kp + base + u * THREADS);
+          for (int u = 0; u < U4; ++u) dst[u] = __ldcg(kp + base + u * THREADS);
         } else {
 #pragma unroll
-          for (int u = 0; u < TOPK_U; ++u) dst[u] = (base + u * THREADS + tid < n) ? __ldcg(kp + base + u * THREADS) : 0ull;
+          for (int u = 0; u < U4; ++u) dst[u] = (base + u * THREADS + tid < n4) ? __ldcg(kp + base + u * THREADS) : make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      auto place_batch = [&](const unsigned long long (&src)[TOPK_U]) {
-        unsigned t[TOPK_U];
+      auto place_batch = [&](const uint4 (&src)[U4], int base) {
         int mine = 0;
 #pragma unroll
-        for (int u = 0; u < TOPK_U; ++u) {
-          t[u] = (unsigned)(src[u] >> 32) - h_lo;    // a zero high word (no key) is below every range: h_lo >= 1
-          mine += t[u] <= h_span ? 1 : 0;
+        for (int u = 0; u < U4; ++u) {               // a zero score word (no box) is below every range: h_lo >= 1
+          mine += (src[u].x - h_lo <= h_span ? 1 : 0) + (src[u].y - h_lo <= h_span ? 1 : 0) +
+                  (src[u].z - h_lo <= h_span ? 1 : 0) + (src[u].w - h_lo <= h_span ? 1 : 0);
         }
         int incl = mine;
 #pragma unroll
@@ -497,19 +502,25 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
         int wbase = 0;
         if (lane == 31 && incl) wbase = atom_shared_add(count_s, incl);
         unsigned addr = cand_s + 8u * (unsigned)(__shfl_sync(0xffffffffu, wbase, 31) + incl - mine);
+        if (mine) {
 #pragma unroll
-        for (int u = 0; u < TOPK_U; ++u) {
-          if (t[u] <= h_span) { st_shared_u64(addr, src[u]); addr += 8u; }
+          for (int u = 0; u < U4; ++u) {
+            const unsigned pos = 4u * (unsigned)(base + u * THREADS + tid);
+            if (src[u].x - h_lo <= h_span) { st_shared_u64(addr, ((unsigned long long)src[u].x << 32) | pos); addr += 8u; }
+            if (src[u].y - h_lo <= h_span) { st_shared_u64(addr, ((unsigned long long)src[u].y << 32) | (pos + 1u)); addr += 8u; }
+            if (src[u].z - h_lo <= h_span) { st_shared_u64(addr, ((unsigned long long)src[u].z << 32) | (pos + 2u)); addr += 8u; }
+            if (src[u].w - h_lo <= h_span) { st_shared_u64(addr, ((unsigned long long)src[u].w << 32) | (pos + 3u)); addr += 8u; }
+          }
         }
       };
-      unsigned long long ka[TOPK_U], kb[TOPK_U];
+      uint4 ka[U4], kb[U4];
       load_batch(ka, 0);
-      for (int base = 0; base < n; base += 2 * BATCH) {
+      for (int base = 0; base < n4; base += 2 * BATCH) {
         load_batch(kb, base + BATCH);
-        place_batch(ka);
-        if (base + BATCH >= n) break;
+        place_batch(ka, base);
+        if (base + BATCH >= n4) break;
         load_batch(ka, base + 2 * BATCH);
-        place_batch(kb);
+        place_batch(kb, base + BATCH);
       }
       __syncthreads();
       // both exact splitters in one set of passes over the candidates: select A counts in the low half of the
@@ -552,25 +563,26 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
     const bool need_hi = first > 0, need_lo = last < n_valid;
     t_hi = ~0ull;
     t_lo = 1ull;
-    if (need_hi) t_hi = radix_select_global<THREADS>(keys, n, first, hist, warp_tot, phase, s_sel);
-    if (need_lo) t_lo = radix_select_global<THREADS>(keys, n, last, hist, warp_tot, phase, s_sel);
+    if (need_hi) t_hi = radix_select_global<THREADS>(skeys, n, first, hist, warp_tot, phase, s_sel);
+    if (need_lo) t_lo = radix_select_global<THREADS>(skeys, n, last, hist, warp_tot, phase, s_sel);
     if (tid == 0) s_count = 0;
     __syncthreads();
     for (int base = 0; base < n; base += THREADS * TOPK_U) {
-      unsigned long long kk[TOPK_U];
+      unsigned kk[TOPK_U];
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
         const int i = base + u * THREADS + tid;
-        kk[u] = (i < n) ? __ldcg(keys + i) : 0ull;
+        kk[u] = (i < n) ? __ldcg(skeys + i) : 0u;
       }
 #pragma unroll
       for (int u = 0; u < TOPK_U; ++u) {
-        const bool take = kk[u] != 0ull && kk[u] >= t_lo && (first == 0 || kk[u] < t_hi);
+        const unsigned long long key = ((unsigned long long)kk[u] << 32) | (unsigned)(base + u * THREADS + tid);
+        const bool take = kk[u] != 0u && key >= t_lo && (first == 0 || key < t_hi);
         const unsigned ballot = __ballot_sync(0xffffffffu, take);
         int wbase = 0;
         if (lane == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (take) cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = kk[u];
+        if (take) cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = key;
       }
     }
     __syncthreads();
@@ -693,7 +705,8 @@ int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, 
   const int n = (int)n_ll;
   if (k > MAX_SPLITS * SORT_T * 8)
     return fail(h, FRCNN_ERR_UNSUPPORTED, "decode_topk: k above 32768 is not supported%s%s");
-  const size_t key_bytes = align_up((size_t)batch * n * sizeof(unsigned long long), 256);
+  const int n_pad = (n + 3) & ~3;
+  const size_t key_bytes = align_up((size_t)batch * n_pad * sizeof(unsigned), 256);
   const size_t box_bytes = align_up((size_t)batch * n * sizeof(BoxI16), 256);
   void* ws = nullptr;
   int rc = arena_get(h, stream, key_bytes + box_bytes, &ws);
@@ -705,7 +718,8 @@ int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, 
   args.rows = rows; args.cols = cols; args.n = n; args.k = k;
   args.div_a = make_fastdiv((unsigned)tab.n);
   args.div_cols = make_fastdiv((unsigned)cols);
-  args.keys = reinterpret_cast<unsigned long long*>(ws);
+  args.skeys = reinterpret_cast<unsigned*>(ws);
+  args.n_pad = n_pad;
   args.boxes = reinterpret_cast<BoxI16*>(reinterpret_cast<char*>(ws) + key_bytes);
   args.dense = reinterpret_cast<float4*>(dense_boxes);
   args.out_boxes = reinterpret_cast<BoxI16*>(out_boxes);
