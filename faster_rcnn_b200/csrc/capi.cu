@@ -258,6 +258,8 @@ int frcnn_proposals(frcnn_handle* h, void* stream, const float* regr, const floa
   if (rc) return rc;
   const long long n_all = (long long)rows * cols * n_anchors;
   const int kk = (int)(k < n_all ? k : n_all);
+  if (kk > FRCNN_NMS_MAX_UNSORTED)
+    return fail(h, FRCNN_ERR_UNSUPPORTED, "proposals: k above FRCNN_NMS_MAX_UNSORTED (use decode_topk + nms_i16)%s%s");
   void *tb = nullptr, *ts = nullptr, *ti = nullptr, *tc = nullptr, *ki = nullptr;
   if ((rc = arena_get(h, st, (size_t)batch * kk * 8, &tb))) return rc;
   if ((rc = arena_get(h, st, (size_t)batch * kk * 4, &ts))) return rc;

@@ -1,22 +1,28 @@
 // K-a: anchors + delta decode + sanitize + validity filter + exact top-k in sorted order, ONE kernel.
 //
-// proposals_kernel: a thread-block cluster of `splits` CTAs per image.
-//   1. decode   every CTA decodes 1/splits of the image's anchors (regr 16 B + cls 4 B in, 64-bit sort key + int16x4 box
-//               out, L2-resident) and histograms its keys by a 2048-bucket monotone digit in shared memory;
+// proposals_kernel: a thread-block cluster of `splits` CTAs per image (up to 16).
+//   1. decode   every CTA decodes 1/splits of the image's anchors (regr 16 B + cls 4 B in; a 32-bit order-preserving
+//               score word + an int16x4 box out, L2-resident; the sort key of an anchor is (score word << 32) | position)
+//               and histograms its score words by a 2048-bucket monotone digit in shared memory;
 //   2. exchange the per-CTA histograms are summed through distributed shared memory (reduce-scatter + all-gather, two
 //               cluster barriers), so every CTA knows how many keys each bucket holds in the whole image;
 //   3. slice    CTA r owns the ranks [r*k/splits, (r+1)*k/splits) of the descending order.  The buckets of its two
-//               bounds follow from the histogram; ONE sweep over the image's keys sends every key strictly between the
-//               two boundary buckets into the slice and parks the boundary buckets' keys in a shared-memory stash, where
-//               the two exact splitters are found together (11-bit radix passes, both selects share one packed histogram);
-//   4. sort     the <= 2047 keys of the slice are sorted by 256 threads holding E keys each in registers (bitonic
-//               network: strides < E are register swaps, < 32E warp shuffles, only >= 32E go through shared memory);
+//               bounds follow from the histogram; ONE sweep over the image's score words (128-bit loads, a thread counts
+//               its hits, one warp scan + one shared atomic per warp place them) collects the CANDIDATES: every key of
+//               the buckets from the lower bound's to the upper bound's.  The two exact splitters are then found among
+//               the candidates only (11-bit radix passes in shared memory, both selects share one packed histogram);
+//   4. sort     candidates outside the splitters become zeros and sink; 256 threads sort M = 256*E keys held E per
+//               thread in registers (bitonic network unrolled at compile time: strides < E are register swaps, < 32E
+//               one shuffle per key, >= 32E one shared-memory exchange with alternating buffers = one barrier);
 //   5. gather   boxes / scores / indices of the slice are written at their final ranks.  Slices need no merge.
 // The bucket digit is the key's top 15 bits (sign, exponent, 6 mantissa bits) taken relative to 1.0 and clamped, i.e. 64
 // buckets per octave over [2^-32, 1): objectness scores are sigmoid outputs, and the plain top-11-bit digit of round 1
 // resolves them into four buckets per octave only (2700-key boundary buckets on uniform scores).  Scores outside the
-// window land in the two clamped end buckets; a bound that falls into one of those, or boundary buckets that outgrow
-// the stash (massive ties), takes the fall-back: exact radix selects over all keys of the image (several sweeps).
+// window land in the two clamped end buckets; a bound that falls into one of those, or candidates that outgrow the
+// buffer (massive ties), take the fall-back: exact radix selects over all keys of the image (several sweeps).
+// Round 1's pair decode_kernel + topk_kernel (global histogram, memset, two launches, three sweeps per slice, one
+// key per thread in the sort) took 25 us for one image and 64 us for 64 (k = 8000, CUDA-graph replay); this kernel
+// takes 14 us and 42 us.
 //
 // Reference semantics (file:line under /root/reference/faster_rcnn):
 //   det_util.py:162-175 anchors (centre = cell index, x1 = x - w//2, x2 = x1 + w)
@@ -651,13 +657,13 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
   if (cluster_pending) cluster_wait();               // no CTA may exit while a peer can still read its shared memory
 }
 
+// probe_only: configure the kernel for this (cluster size, shared memory) once per handle and report whether a cluster
+// of that size can be resident at all; the answer is cached in the handle, so a steady-state call is one launch.
 template <int THREADS, int E>
 static int launch_proposals(frcnn_handle* h, cudaStream_t stream, const ProposalArgs& args, const AnchorTable& tab,
                             int batch, bool probe_only) {
   const size_t smem = (size_t)(SORT_T * E + SORT_T + args.w_cap) * sizeof(unsigned long long);
   auto kernel = proposals_kernel<THREADS, E>;
-  FRCNN_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (args.splits > 8) FRCNN_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(batch * args.splits));
   cfg.blockDim = dim3(THREADS);
@@ -671,9 +677,17 @@ static int launch_proposals(frcnn_handle* h, cudaStream_t stream, const Proposal
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (probe_only) {
-    int clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); clusters = 0; }
-    return clusters > 0 ? FRCNN_OK : FRCNN_ERR_UNSUPPORTED;
+    constexpr int LOG_E = E == 1 ? 0 : E == 2 ? 1 : E == 4 ? 2 : 3;
+    unsigned char& state = h->proposals_cfg[THREADS == 1024 ? 1 : 0][LOG_E][args.splits];
+    if (state == 0) {
+      FRCNN_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (args.splits > 8) FRCNN_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      int clusters = 0;
+      cfg.gridDim = dim3((unsigned)args.splits);
+      if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+      state = clusters > 0 ? 1 : 2;
+    }
+    return state == 1 ? FRCNN_OK : FRCNN_ERR_UNSUPPORTED;
   }
   FRCNN_CUDA(h, cudaLaunchKernelEx(&cfg, kernel, args, tab));
   FRCNN_LAUNCH_CHECK(h, "proposals_kernel");

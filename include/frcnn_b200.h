@@ -95,7 +95,9 @@ FRCNN_API long long frcnn_launch_count(frcnn_handle* h);
  *   i32 (flat anchor index), out_count [batch] i32.  Order: score descending,
  *   ties by descending anchor index; rows >= count are zero / index -1.
  *   dense_boxes (optional, may be NULL) [batch,R*C*A,4] f32 receives every
- *   decoded+sanitized box (the return value of _get_rois). */
+ *   decoded+sanitized box (the return value of _get_rois).
+ *   Capacity: k <= 32768 (FRCNN_ERR_UNSUPPORTED above); any float scores are
+ *   ranked exactly, the fast path is tuned for scores in [2^-32, 1). */
 FRCNN_API int frcnn_decode_topk(frcnn_handle* h, void* stream, const float* regr, const float* cls,
                       const int32_t* anchor_hw_host, int rows, int cols, int n_anchors,
                       int stride, int k, int batch, int16_t* out_boxes, float* out_scores,
@@ -131,7 +133,9 @@ FRCNN_API int frcnn_nms_f64(frcnn_handle* h, void* stream, const double* boxes, 
 /* ---- fused proposal stage: K-a feeding K-b without leaving the device.
  * Replaces DetTrainingManager.get_det_inputs / _process up to nms
  * (det_util.py:63-77, :136-158).  out_rois [batch,max_boxes,4] i16,
- * out_scores [batch,max_boxes] f32, out_count [batch] i32. */
+ * out_scores [batch,max_boxes] f32, out_count [batch] i32.
+ * min(k, R*C*A) <= FRCNN_NMS_MAX_UNSORTED: tied scores make the top-k list
+ * "unsorted" for K-b, and the fused call has no way to report K-b's flag. */
 FRCNN_API int frcnn_proposals(frcnn_handle* h, void* stream, const float* regr, const float* cls,
                     const int32_t* anchor_hw_host, int rows, int cols, int n_anchors, int stride,
                     int k, double thresh, int max_boxes, int batch, int16_t* out_rois,

@@ -470,3 +470,21 @@ def test_decode_topk_batch_uses_narrow_ctas(ops):
         assert n == len(wb), i
         assert np.array_equal(index[i, :n], widx) and np.array_equal(boxes[i, :n], wb) and np.array_equal(scores[i, :n], wp), i
         assert np.all(index[i, n:] == -1)
+
+
+def test_decode_topk_repeated_launches_are_identical(ops):
+    """proposals_kernel exchanges histograms between the CTAs of a cluster; every launch must give the same answer
+    whatever the timing (L2 flushed or hot, wide or narrow CTAs, back-to-back launches)."""
+    import torch
+    dims = O.anchor_table([128, 256, 512])
+    from faster_rcnn_b200 import synth
+    junk = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")
+    for rows, cols, k, b in [(10, 12, 8000, 1), (38, 63, 8000, 1), (20, 20, 1500, 3), (38, 63, 8000, 24)]:
+        pairs = [synth.rpn_outputs(rows, cols, 9, 800 + i, clustered=bool(i % 2)) for i in range(b)]
+        cls, regr = dev(np.concatenate([p[0] for p in pairs])), dev(np.concatenate([p[1] for p in pairs]))
+        ref = [t.clone() for t in ops.decode_topk(regr, cls, dims, 16, k)]
+        for rep in range(60):
+            if rep % 3 == 1:
+                junk.fill_(rep)
+            got = ops.decode_topk(regr, cls, dims, 16, k)
+            assert all(torch.equal(a, g) for a, g in zip(ref, got)), (rows, cols, k, b, rep)
