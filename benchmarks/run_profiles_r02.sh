@@ -19,5 +19,9 @@ timeout 300 $NCU -k regex:roi_bwd --launch-skip 6 -c 3 -o gpurun_out/r02_roi_bwd
     python benchmarks/roi_one.py --dir bwd --mode resize --rois 2000 --batch 1 > /dev/null 2>&1
 timeout 300 $NCU -k regex:nms_i16 --launch-skip 2 -c 1 -o gpurun_out/r02_nms_train_b1 \
     python benchmarks/prop_one.py 1 12000 2000 > /dev/null 2>&1
+timeout 300 $NCU -k regex:proposals_kernel --launch-skip 3 -c 1 -o gpurun_out/r02_proposals_b1 \
+    python benchmarks/prop_one.py 1 8000 300 > /dev/null 2>&1
+timeout 300 $NCU -k regex:proposals_kernel --launch-skip 3 -c 1 -o gpurun_out/r02_proposals_b64 \
+    python benchmarks/prop_one.py 64 8000 300 > /dev/null 2>&1
 timeout 600 python benchmarks/stages.py --iters 30 --json gpurun_out/r02_stages.json > gpurun_out/r02_stages.log 2>&1
 ls -la gpurun_out/r02_*
