@@ -47,20 +47,55 @@ def case_nms(rng):
     return ok, dict(kind="nms", n=n, thresh=thresh, max_boxes=max_boxes)
 
 
+def _scores(rng, shape):
+    """objectness of many shapes: the rank-uniform synthetic ones, and arrays that stress proposals_kernel's bucket window
+    ([2^-32, 1), 64 buckets per octave): logits, saturated sigmoids, tiny values, few distinct values, narrow bands."""
+    n = int(np.prod(shape))
+    u = (rng.permutation(n).astype(np.float64) + 0.5) / n
+    kind = int(rng.integers(0, 8))
+    if kind == 0:
+        v = (u - rng.random()) * float(rng.choice([4.0, 30.0, 200.0]))                    # logits
+    elif kind == 1:
+        v = 1.0 / (1.0 + np.exp(-(u - rng.random()) * float(rng.choice([10.0, 40.0, 120.0]))))   # sigmoid, saturating
+    elif kind == 2:
+        v = u * float(rng.choice([1e-12, 1e-6, 1e-3]))
+    elif kind == 3:
+        v = np.minimum(u * float(rng.choice([1.2, 2.0, 8.0])), 1.0)                       # many exact 1.0
+    elif kind == 4:
+        v = float(rng.choice([0.3, 0.75, 0.999])) + u * float(rng.choice([1e-6, 1e-4, 1e-2]))   # one or two buckets
+    elif kind == 5:
+        v = np.round(u * int(rng.choice([1, 2, 7, 100]))) / 100.0                          # few distinct values incl. 0
+    elif kind == 6:
+        v = np.exp(-u * float(rng.choice([5.0, 30.0, 80.0])))                             # log-uniform over many octaves
+    else:
+        v = u
+    return v.astype(np.float32).reshape(shape)
+
+
 def case_proposals(rng):
     rows, cols = int(rng.integers(1, 40)), int(rng.integers(1, 70))
     scales = [128, 256, 512] if rng.random() < 0.6 else [16, 32, 64, 128, 256, 512]
     dims = O.anchor_table(scales)
-    cls, regr = synth.rpn_outputs(rows, cols, len(dims), int(rng.integers(1 << 30)), clustered=bool(rng.random() < 0.5))
-    k = int(rng.choice([1, 50, 1024, 2049, 8000, 12000]))
+    b = int(rng.choice([1, 1, 1, 2, 5, 20]))
+    pairs = [synth.rpn_outputs(rows, cols, len(dims), int(rng.integers(1 << 30)), clustered=bool(rng.random() < 0.5)) for _ in range(b)]
+    cls, regr = np.concatenate([p[0] for p in pairs]), np.concatenate([p[1] for p in pairs])
+    if rng.random() < 0.6:
+        cls = np.stack([_scores(rng, cls.shape[1:]) for _ in range(b)])
+    k = int(rng.choice([1, 50, 1024, 2049, 8000, 12000, 16384]))
     max_boxes = int(rng.choice([1, 10, 300, 2000]))
-    dense = host(ops.decode_topk(dev(regr), dev(cls), dims, 16, k, want_dense=True)[4])[0]
-    wb, wp, _ = O.topk_proposals(dense.copy(), cls.reshape(-1), k)
-    pick = O.greedy_nms(wb, wp, 0.7, max_boxes) if len(wb) else np.zeros(0, np.int64)
+    boxes, scores_k, index, cnt, dense = [host(t) for t in ops.decode_topk(dev(regr), dev(cls), dims, 16, k, want_dense=True)]
     rois, scores, count = ops.proposals(dev(regr), dev(cls), dims, 16, k, 0.7, max_boxes)
-    m = int(host(count)[0])
-    ok = m == len(pick) and np.array_equal(host(rois)[0, :m], wb[pick]) and np.array_equal(host(scores)[0, :m], wp[pick])
-    return ok, dict(kind="proposals", rows=rows, cols=cols, a=len(dims), k=k, max_boxes=max_boxes)
+    rois, scores, count = host(rois), host(scores), host(count)
+    ok = True
+    for i in range(b):
+        wb, wp, widx = O.topk_proposals(dense[i].copy(), cls[i].reshape(-1), k)
+        n = int(cnt[i])
+        ok = ok and n == len(wb) and np.array_equal(index[i, :n], widx) and np.array_equal(boxes[i, :n], wb) \
+            and np.array_equal(scores_k[i, :n], wp) and bool(np.all(index[i, n:] == -1))
+        pick = O.greedy_nms(wb, wp, 0.7, max_boxes) if len(wb) else np.zeros(0, np.int64)
+        m = int(count[i])
+        ok = ok and m == len(pick) and np.array_equal(rois[i, :m], wb[pick]) and np.array_equal(scores[i, :m], wp[pick])
+    return ok, dict(kind="proposals", rows=rows, cols=cols, a=len(dims), k=k, max_boxes=max_boxes, batch=b)
 
 
 def case_roi(rng):
@@ -177,9 +212,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=300)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--only", default="", help="comma-separated case kinds, e.g. proposals,nms")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     kinds = [case_nms, case_proposals, case_roi, case_labels, case_label_rois, case_postprocess, case_image]
+    if args.only:
+        kinds = [f for f in kinds if f.__name__[5:] in args.only.split(",")]
     counts, failures = {}, []
     for i in range(args.cases):
         fn = kinds[i % len(kinds)]
