@@ -73,28 +73,6 @@ __device__ __forceinline__ unsigned fast_div(unsigned i, FastDiv f) {
   return (t + ((i - t) >> f.s1)) >> f.s2;
 }
 
-// np_expf (common.cuh) without branches: the three special ranges become selects and the final scaling by 2^q is two
-// multiplications by exact powers of two (one rounding, like scalbnf; |q| <= 150 inside the evaluated range).
-__device__ __forceinline__ float np_expf_inline(float x) {
-  float q = __fmul_rn(x, 1.44269504088896340736f);
-  q = __fsub_rn(__fadd_rn(q, 12582912.0f), 12582912.0f);
-  float r = __fmaf_rn(q, -6.93145752e-1f, x);
-  r = __fmaf_rn(q, -1.42860677e-6f, r);
-  float num = __fmaf_rn(5.082762527590693718096e-04f, r, 6.757896990527504603057e-03f);
-  num = __fmaf_rn(num, r, 5.114512081637298353406e-02f);
-  num = __fmaf_rn(num, r, 2.473615434895520810817e-01f);
-  num = __fmaf_rn(num, r, 7.257664613233124478488e-01f);
-  num = __fmaf_rn(num, r, 9.999999999980870924916e-01f);
-  float den = __fmaf_rn(2.159509375685829852307e-02f, r, -2.742335390411667452936e-01f);
-  den = __fmaf_rn(den, r, 1.0f);
-  float v = __fdiv_rn(num, den);
-  const int qi = (int)q, h1 = qi >> 1, h2 = qi - h1;
-  v = __fmul_rn(__fmul_rn(v, __int_as_float((h1 + 127) << 23)), __int_as_float((h2 + 127) << 23));
-  v = x > 88.72283935546875f ? __int_as_float(0x7f800000) : v;
-  v = x < -103.97208404541015625f ? 0.0f : v;
-  return x != x ? x : v;
-}
-
 // np.maximum / np.minimum (NaN-propagating) as single instructions
 __device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
@@ -305,7 +283,7 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
   __shared__ unsigned hist[TOPK_BINS];               // bucket histogram of the whole image
   __shared__ unsigned warp_tot[2][32];
   __shared__ int s_count, s_sel[6], s_total;
-  __shared__ short s_aw[FRCNN_MAX_ANCHORS], s_ah[FRCNN_MAX_ANCHORS];
+  __shared__ int4 s_anchor[FRCNN_MAX_ANCHORS];       // (bits of float w, bits of float h, -(w >> 1), -(h >> 1)) in feature cells
 
   const int splits = p.splits, n = p.n, k = p.k;
   const int img = blockIdx.x / splits, part = blockIdx.x - img * splits;
@@ -316,7 +294,8 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
   int phase = 0;
 
   for (int i = tid; i < TOPK_BINS; i += THREADS) hist_own[i] = 0u;
-  if (tid < tab.n) { s_aw[tid] = (short)tab.w[tid]; s_ah[tid] = (short)tab.h[tid]; }
+  if (tid < tab.n)
+    s_anchor[tid] = make_int4(__float_as_int((float)tab.w[tid]), __float_as_int((float)tab.h[tid]), -(tab.w[tid] >> 1), -(tab.h[tid] >> 1));
   if (tid == 0) s_count = 0;
   __syncthreads();
 
@@ -334,13 +313,13 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
       const int a = i - (int)loc * tab.n;
       const unsigned cy_i = fast_div(loc, p.div_cols);
       const int cx_i = (int)loc - (int)cy_i * p.cols;
-      const int aw = s_aw[a], ah = s_ah[a];
+      const int4 an = s_anchor[a];
 
       // anchors are integer valued -> exact in float32
-      float x = (float)(cx_i - (aw >> 1));
-      float y = (float)((int)cy_i - (ah >> 1));
-      float w = (float)aw;     // (x + aw) - x
-      float hgt = (float)ah;
+      float x = (float)(cx_i + an.z);
+      float y = (float)((int)cy_i + an.w);
+      float w = __int_as_float(an.x);     // (x + aw) - x
+      float hgt = __int_as_float(an.y);
 
       // deltas / [10, 10, 5, 5] (util.py:118-121): one range guard for the four, the generic division outside it
       float tx = div_const_core<10>(r.x), ty = div_const_core<10>(r.y);
@@ -358,8 +337,13 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
       y = __fadd_rn(y, __fmul_rn(hgt, 0.5f));
       x = __fadd_rn(x, __fmul_rn(tx, w));
       y = __fadd_rn(y, __fmul_rn(ty, hgt));
-      w = __fmul_rn(w, np_expf_inline(tw));
-      hgt = __fmul_rn(hgt, np_expf_inline(th));
+      if (fabsf(tw) <= EXP_MID_LIMIT && fabsf(th) <= EXP_MID_LIMIT) {
+        w = __fmul_rn(w, np_expf_mid(tw));
+        hgt = __fmul_rn(hgt, np_expf_mid(th));
+      } else {                                       // huge deltas, NaN
+        w = __fmul_rn(w, np_expf(tw));
+        hgt = __fmul_rn(hgt, np_expf(th));
+      }
       x = __fsub_rn(x, __fmul_rn(w, 0.5f));
       y = __fsub_rn(y, __fmul_rn(hgt, 0.5f));
       x = rintf(x); y = rintf(y); w = rintf(w); hgt = rintf(hgt);     // np.round: half to even
