@@ -27,6 +27,8 @@ def ops():
     ((37, 53), (111, 97), 1, 3, True),
     ((5, 4), (9, 13), 4, 1, False),             # taps clamped on every side
     ((600, 800), (600, 800), 3, 1, False),      # identity
+    ((640, 480), (90, 70), 3, 2, True),         # 7x reduction: eight output rows span > 40 source rows, per-pixel kernel
+    ((333, 47), (61, 301), 2, 1, False),        # reduced 5.5x in y (tile limit), enlarged 6.4x in x, ragged tiles
 ])
 def test_resize_kernel_equals_oracle(ops, src, dst, cn, batch, flip):
     rng = np.random.default_rng(src[0] + dst[1] + cn)
