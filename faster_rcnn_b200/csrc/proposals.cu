@@ -445,12 +445,13 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
     const bool one_bucket = da == db;
     bool sel_a = need_hi && rest_a != cnt_a;         // rest == cnt: the bucket goes to one side whole, nothing to select
     bool sel_b = need_lo && rest_b != cnt_b;
-    // candidates = every key of the buckets [d_first .. d_last]: the boundary buckets that need a select, and everything
-    // between the two bounds; a boundary bucket that lies on the far side whole is left out
-    const int d_last = (sel_a || (one_bucket && sel_b)) ? da : da - 1;
-    const int d_first = need_lo ? ((sel_b || one_bucket || rest_b == cnt_b) ? db : db + 1) : 0;
-    const int extra_a = (d_last == da && need_hi) ? rest_a : 0;                          // candidates above the slice
-    const int extra_b = (need_lo && d_first == db && !(rest_b == cnt_b)) ? cnt_b - rest_b : 0;   // ... and below it
+    // candidates = every key of the buckets [d_first .. d_last]: everything between the two bounds, the upper bound's
+    // bucket if it has to be split (otherwise it belongs to the slices above whole), and the lower bound's bucket
+    // (split, or this slice's whole)
+    const int d_last = sel_a ? da : da - 1;
+    const int d_first = need_lo ? db : 0;
+    const int extra_a = sel_a ? rest_a : 0;                  // candidates above the slice
+    const int extra_b = sel_b ? cnt_b - rest_b : 0;          // ... and below it
     n_cand = (last - first) + extra_a + extra_b;
     const bool clamped = (sel_a && (da == 0 || da == TOPK_BINS - 1)) || (sel_b && (db == 0 || db == TOPK_BINS - 1));
     if (need_hi) t_hi = fine_prefix(da);
