@@ -732,9 +732,16 @@ int launch_decode_topk(frcnn_handle* h, cudaStream_t stream, const float* regr, 
   // threads while batch * splits fits the SM count, 256-thread CTAs (four or more per SM) beyond.
   int splits = (k + 999) / 1000;
   const int for_decode = (n + 4095) / 4096;
-  if (splits < for_decode) splits = for_decode < 8 ? for_decode : 8;
+  if (splits < 8 && splits < for_decode) splits = for_decode < 8 ? for_decode : 8;
   if ((long long)batch * MAX_SPLITS <= h->sm_count && n >= 4096) splits = MAX_SPLITS;
   if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+  // Large batches run 256-thread CTAs, four per SM (three with 2048-key sorts).  When 1000-rank slices need a second
+  // wave of CTAs but 2000-rank slices fit one, take those: half the sweeps, and no 30 %-full tail wave (64 images,
+  // k = 12000: 61.8 -> 49.0 us at VOC shapes, 125.9 -> 91.3 us at KITTI's 64 k anchors; k = 8000 fits one wave as it is).
+  {
+    const int half = (k + 1999) / 2000;
+    if ((long long)batch * splits > 4LL * h->sm_count && (long long)batch * half <= 3LL * h->sm_count && half >= 1) splits = half;
+  }
   splits = env_int("FRCNN_TOPK_SPLITS", splits);      // experiment knobs (benchmarks/prop_one.py)
   if (splits < 1) splits = 1;
   if (splits > MAX_SPLITS) splits = MAX_SPLITS;
