@@ -22,7 +22,7 @@
 // buffer (massive ties), take the fall-back: exact radix selects over all keys of the image (several sweeps).
 // Round 1's pair decode_kernel + topk_kernel (global histogram, memset, two launches, three sweeps per slice, one
 // key per thread in the sort) took 25 us for one image and 64 us for 64 (k = 8000, CUDA-graph replay); this kernel
-// takes 14 us and 42 us.
+// takes 14 us and 40 us.
 //
 // Reference semantics (file:line under /root/reference/faster_rcnn):
 //   det_util.py:162-175 anchors (centre = cell index, x1 = x - w//2, x2 = x1 + w)
