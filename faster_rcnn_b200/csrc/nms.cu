@@ -520,10 +520,11 @@ int launch_nms_i16(frcnn_handle* h, cudaStream_t stream, const int16_t* boxes, c
   if (max_keep >= 1024) {
     // measured: 16 (non-portable cluster size) at batch 1: 0.81 -> 0.74 ms at 12000 -> 2000; 2 at batch 64
     while (cl < 16 && (long long)batch * cl * 2 <= h->sm_count) cl <<= 1;
-    if (getenv("FRCNN_NMS_CL")) cl = atoi(getenv("FRCNN_NMS_CL"));
   } else if (max_keep >= 256) {
     while (cl < 2 && (long long)batch * cl * 2 <= h->sm_count) cl <<= 1;
   }
+  if (getenv("FRCNN_NMS_CL")) cl = atoi(getenv("FRCNN_NMS_CL"));     // experiment knob
+  if (cl < 1 || cl > 16 || (cl & (cl - 1))) cl = 1;
   const int keep_local = (max_keep + cl - 1) / cl;
   const size_t smem = align_up((size_t)buf_elems * 8, 16) + (size_t)keep_local * (16 + 4) + (size_t)max_keep * 4 + 16;
   if (smem + 2048 > (size_t)h->max_smem_optin)
