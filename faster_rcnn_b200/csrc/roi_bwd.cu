@@ -22,6 +22,8 @@
 // twice the bytes are in flight per SM.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "roi_common.cuh"
 
 namespace frcnn {
@@ -65,8 +67,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int MODE>
 __global__ void __launch_bounds__(256)
 roi_bwd_mask_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, int H, int W, int P, int blocks_y,
-                    int blocks_x, uint8_t* __restrict__ ymask, uint8_t* __restrict__ xmask) {
+                    int blocks_x, uint8_t* __restrict__ ymask, uint8_t* __restrict__ xmask, unsigned* __restrict__ counter) {
   const int r = blockIdx.x * 256 + threadIdx.x, ab = blockIdx.y, img = blockIdx.z;   // ab: block rows, then block columns
+  if (r == 0 && ab == 0 && img == 0) *counter = 0u;      // the plan kernel's bump allocator (saves a memset node per call)
   if (r >= n_pad) return;
   const bool is_y = ab < blocks_y;
   uint8_t* dst = is_y ? ymask + ((size_t)img * blocks_y + ab) * n_pad : xmask + ((size_t)img * blocks_x + (ab - blocks_y)) * n_pad;
@@ -174,13 +177,18 @@ roi_bwd_plan_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, 
   for (int round_lo = r_lo; round_lo < r_hi; round_lo += PLAN_ROUND) {
     const int round_hi = min(r_hi, round_lo + PLAN_ROUND);
     int nq = 0, ne = 0;                                  // queued RoIs / entries of this round (warp-uniform)
-    for (int r0 = round_lo; r0 < round_hi; r0 += 32) {
-      const int r = r0 + lane;
-      unsigned my = 0u, mx = 0u;
-      if (r < round_hi) {
-        my = ym[r];
-        mx = xm[r];
-      }
+    // the round's mask bytes are fetched up front: eight dependent L2 round trips became one (4.4 k -> 1.2 k cycles)
+    unsigned pre_y[PLAN_ROUND / 32], pre_x[PLAN_ROUND / 32];
+#pragma unroll
+    for (int it = 0; it < PLAN_ROUND / 32; ++it) {
+      const int r = round_lo + it * 32 + lane;
+      pre_y[it] = r < round_hi ? (unsigned)ym[r] : 0u;
+      pre_x[it] = r < round_hi ? (unsigned)xm[r] : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < PLAN_ROUND / 32; ++it) {
+      const int r = round_lo + it * 32 + lane;
+      const unsigned my = pre_y[it], mx = pre_x[it];
       const int cnt = __popc(my) * __popc(mx);
       const unsigned hits = __ballot_sync(0xffffffffu, cnt > 0);
       if (hits == 0u) continue;
@@ -199,47 +207,75 @@ roi_bwd_plan_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, 
       ne += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
-    for (int e = lane; e < ne; e += 32) {
-      int lo = 0, hi = nq;                               // last queued RoI whose first entry is <= e
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)qstart[mid] <= e) lo = mid; else hi = mid;
-      }
-      const unsigned rec = qroi[lo];
-      const int r = (int)(rec & 0xffffu);
-      unsigned my = (rec >> 16) & 0xffu, mx = rec >> 24;
-      const int k = e - (int)qstart[lo], nx = __popc(mx);
-      const int iy = (int)((unsigned)k * c_div_magic[nx]) >> 9, ix = k - iy * nx;
-      for (int i = 0; i < iy; ++i) my &= my - 1u;
-      for (int i = 0; i < ix; ++i) mx &= mx - 1u;
-      const int ph = __ffs(my) - 1, pw = __ffs(mx) - 1;
-      const unsigned row = (unsigned)((r * P + ph) * P + pw);
-      const unsigned pos = pos_warp + (unsigned)e;
-      if (MODE == ROI_MAX_COMPACT) {
-        // the block's four cells as arg-max codes of THIS bin ((dy << 4) | dx from the bin's first cell); a cell the
-        // code cannot describe (outside [0,16) in either direction) gets 0xffff, which no stored byte equals
-        const Crop c = load_crop(rois, dtype, (size_t)img * N + r, W, H);
-        const int ya = c.y1 + (ph * c.h) / P, xa = c.x1 + (pw * c.w) / P;
-        unsigned code[4];
+    // Long lists: four entries per lane and step, their chains (queue search, crop load, tap weights) independent of
+    // each other; short lists (most blocks: a few dozen entries per warp) one entry per lane, or three quarters of the
+    // lanes would execute the four-wide step for nothing.
+    auto generate = [&](auto eu_tag) {
+    constexpr int EU = decltype(eu_tag)::value;
+    for (int e0 = lane; e0 < ne; e0 += 32 * EU) {
+      unsigned rec[EU];
+      int kk[EU];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int dy = Y0 + (q >> 1) - ya, dx = X0 + (q & 1) - xa;
-          code[q] = ((unsigned)dy < 16u && (unsigned)dx < 16u) ? (unsigned)((dy << 4) | dx) : 0xffffu;
+      for (int u = 0; u < EU; ++u) {
+        const int e = min(e0 + 32 * u, ne - 1);          // lanes past the end repeat the last entry and do not store
+        int lo = 0;                                      // last queued RoI whose first entry is <= e
+#pragma unroll
+        for (int step = PLAN_ROUND / 2; step > 0; step >>= 1) {
+          const int mid = lo + step;
+          if (mid < nq && (int)qstart[mid] <= e) lo = mid;
         }
-        ent_idx[pos] = row;
-        reinterpret_cast<uint4*>(ent_w)[pos] = make_uint4(code[0], code[1], code[2], code[3]);
-      } else if (MODE == FRCNN_ROI_RESIZE) {
-        const Crop c = load_crop(rois, dtype, (size_t)img * N + r, W, H);
-        float wy0, wy1, wx0, wx1;
-        const unsigned hy = axis_weights(ph, (float)c.h / (float)P, c.h, c.y1 - Y0, wy0, wy1);
-        const unsigned hx = axis_weights(pw, (float)c.w / (float)P, c.w, c.x1 - X0, wx0, wx1);
-        const unsigned mask = ((hy & 1u) ? hx : 0u) | ((hy & 2u) ? hx << 2 : 0u);
-        ent_idx[pos] = row | (mask << ENT_MASK_SHIFT);
-        ent_w[pos] = make_float4(__fmul_rn(wy0, wx0), __fmul_rn(wy0, wx1), __fmul_rn(wy1, wx0), __fmul_rn(wy1, wx1));
-      } else {
-        ent_idx[pos] = row;
+        rec[u] = qroi[lo];
+        kk[u] = e - (int)qstart[lo];
+      }
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        const int e = e0 + 32 * u;
+        const int r = (int)(rec[u] & 0xffffu);
+        unsigned my = (rec[u] >> 16) & 0xffu, mx = rec[u] >> 24;
+        const int k = kk[u], nx = __popc(mx);
+        const int iy = (int)((unsigned)k * c_div_magic[nx]) >> 9, ix = k - iy * nx;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {                    // masks have at most 8 bits: drop the iy / ix lowest ones
+          if (i < iy) my &= my - 1u;
+          if (i < ix) mx &= mx - 1u;
+        }
+        const int ph = __ffs(my) - 1, pw = __ffs(mx) - 1;
+        const unsigned row = (unsigned)((r * P + ph) * P + pw);
+        const unsigned pos = pos_warp + (unsigned)e;
+        const bool live = e < ne;
+        if (MODE == ROI_MAX_COMPACT) {
+          // the block's four cells as arg-max codes of THIS bin ((dy << 4) | dx from the bin's first cell); a cell the
+          // code cannot describe (outside [0,16) in either direction) gets 0xffff, which no stored byte equals
+          const Crop c = load_crop(rois, dtype, (size_t)img * N + r, W, H);
+          const int ya = c.y1 + (ph * c.h) / P, xa = c.x1 + (pw * c.w) / P;
+          unsigned code[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int dy = Y0 + (q >> 1) - ya, dx = X0 + (q & 1) - xa;
+            code[q] = ((unsigned)dy < 16u && (unsigned)dx < 16u) ? (unsigned)((dy << 4) | dx) : 0xffffu;
+          }
+          if (live) {
+            ent_idx[pos] = row;
+            reinterpret_cast<uint4*>(ent_w)[pos] = make_uint4(code[0], code[1], code[2], code[3]);
+          }
+        } else if (MODE == FRCNN_ROI_RESIZE) {
+          const Crop c = load_crop(rois, dtype, (size_t)img * N + r, W, H);
+          float wy0, wy1, wx0, wx1;
+          const unsigned hy = axis_weights(ph, (float)c.h / (float)P, c.h, c.y1 - Y0, wy0, wy1);
+          const unsigned hx = axis_weights(pw, (float)c.w / (float)P, c.w, c.x1 - X0, wx0, wx1);
+          const unsigned mask = ((hy & 1u) ? hx : 0u) | ((hy & 2u) ? hx << 2 : 0u);
+          if (live) {
+            ent_idx[pos] = row | (mask << ENT_MASK_SHIFT);
+            ent_w[pos] = make_float4(__fmul_rn(wy0, wx0), __fmul_rn(wy0, wx1), __fmul_rn(wy1, wx0), __fmul_rn(wy1, wx1));
+          }
+        } else {
+          if (live) ent_idx[pos] = row;
+        }
       }
     }
+    };
+    if (ne > 64) generate(std::integral_constant<int, 4>());
+    else generate(std::integral_constant<int, 1>());
     __syncwarp();                                        // the queue is rewritten by the next round
     pos_warp += (unsigned)ne;
   }
@@ -525,7 +561,6 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   if ((rc = arena_get(h, stream, (size_t)batch * blocks_x * n_pad, &p_xm))) return rc;
   if ((rc = arena_get(h, stream, (size_t)cap * sizeof(unsigned), &p_idx))) return rc;
   if ((mode == FRCNN_ROI_RESIZE || compact) && (rc = arena_get(h, stream, (size_t)cap * sizeof(float4), &p_w))) return rc;
-  FRCNN_CUDA(h, cudaMemsetAsync(p_cnt, 0, 4, stream));
   dim3 mgrid((n_pad + 255) / 256, blocks_y + blocks_x, batch), pgrid(n_blocks, batch);
   uint8_t *ym = static_cast<uint8_t*>(p_ym), *xm = static_cast<uint8_t*>(p_xm);
   // plan CTAs: 8 warps sweep 2000 RoIs in one queue round each; short RoI lists take smaller CTAs (38912 of them at C1 x 64)
@@ -534,13 +569,13 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
       rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, (unsigned)cap, ym, xm, static_cast<unsigned*>(p_cnt),       \
       static_cast<int2*>(p_tab), static_cast<unsigned*>(p_idx), static_cast<float4*>(p_w))
   if (mode == FRCNN_ROI_RESIZE) {
-    roi_bwd_mask_kernel<FRCNN_ROI_RESIZE><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
+    roi_bwd_mask_kernel<FRCNN_ROI_RESIZE><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm, static_cast<unsigned*>(p_cnt));
     if (N > 1024) FRCNN_PLAN(FRCNN_ROI_RESIZE, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_RESIZE, 4); else FRCNN_PLAN(FRCNN_ROI_RESIZE, 2);
   } else if (compact) {
-    roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
+    roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm, static_cast<unsigned*>(p_cnt));
     if (N > 1024) FRCNN_PLAN(ROI_MAX_COMPACT, 8); else if (N > 256) FRCNN_PLAN(ROI_MAX_COMPACT, 4); else FRCNN_PLAN(ROI_MAX_COMPACT, 2);
   } else {
-    roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm);
+    roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm, static_cast<unsigned*>(p_cnt));
     if (N > 1024) FRCNN_PLAN(FRCNN_ROI_MAX, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_MAX, 4); else FRCNN_PLAN(FRCNN_ROI_MAX, 2);
   }
 #undef FRCNN_PLAN
