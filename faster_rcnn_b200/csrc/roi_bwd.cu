@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256)
 roi_bwd_mask_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, int H, int W, int P, int blocks_y,
                     int blocks_x, uint8_t* __restrict__ ymask, uint8_t* __restrict__ xmask, unsigned* __restrict__ counter) {
   const int r = blockIdx.x * 256 + threadIdx.x, ab = blockIdx.y, img = blockIdx.z;   // ab: block rows, then block columns
-  if (r == 0 && ab == 0 && img == 0) *counter = 0u;      // the plan kernel's bump allocator (saves a memset node per call)
+  if (r == 0 && ab == 0) counter[img] = 0u;              // the plan kernel's bump allocators (saves a memset node per call)
   if (r >= n_pad) return;
   const bool is_y = ab < blocks_y;
   uint8_t* dst = is_y ? ymask + ((size_t)img * blocks_y + ab) * n_pad : xmask + ((size_t)img * blocks_x + (ab - blocks_y)) * n_pad;
@@ -122,7 +122,10 @@ __constant__ unsigned short c_div_magic[9] = {0, 512, 256, 171, 128, 103, 86, 74
 // with one lane per RoI left ~5 of 32 lanes busy and was 4x slower.
 constexpr int PLAN_ROUND = 256;              // RoIs per queue round and warp
 
-template <int MODE, int WARPS>
+// PER_WARP: every warp of the CTA plans a block of its own (short RoI lists, e.g. 320 RoIs x 64 images = 38912 blocks:
+// with one CTA per block the launch is a queue of tiny CTAs whose barriers and allocation round trip are exposed 260
+// times per SM; with independent warps four times as many chains are in flight).
+template <int MODE, int WARPS, bool PER_WARP>
 __global__ void __launch_bounds__(WARPS * 32)
 roi_bwd_plan_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, int H, int W, int P, int blocks_y,
                     int blocks_x, unsigned capacity, const uint8_t* __restrict__ ymask,
@@ -132,14 +135,17 @@ roi_bwd_plan_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, 
   __shared__ unsigned s_wbase[WARPS];
   __shared__ unsigned s_qroi[WARPS][PLAN_ROUND];            // RoI index | my << 16 | mx << 24
   __shared__ unsigned short s_qstart[WARPS][PLAN_ROUND];    // first entry of the RoI inside the round
-  const int b = blockIdx.x, img = blockIdx.y, n_blocks = blocks_y * blocks_x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int VW = PER_WARP ? 1 : WARPS;                  // warps that share one block's RoIs
+  const int vwarp = PER_WARP ? 0 : warp;
+  const int b = PER_WARP ? blockIdx.x * WARPS + warp : blockIdx.x, img = blockIdx.y, n_blocks = blocks_y * blocks_x;
+  if (PER_WARP && b >= n_blocks) return;
   const int by = b / blocks_x, bx = b - by * blocks_x;
   const int Y0 = by * BLK, X0 = bx * BLK;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint8_t* ym = ymask + ((size_t)img * blocks_y + by) * n_pad;
   const uint8_t* xm = xmask + ((size_t)img * blocks_x + bx) * n_pad;
-  const int per_warp = ((N + WARPS - 1) / WARPS + 31) / 32 * 32;
-  const int r_lo = min(n_pad, warp * per_warp), r_hi = min(n_pad, r_lo + per_warp);   // padding masks are zero
+  const int per_warp = ((N + VW - 1) / VW + 31) / 32 * 32;
+  const int r_lo = min(n_pad, vwarp * per_warp), r_hi = min(n_pad, r_lo + per_warp);   // padding masks are zero
 
   // pass 1: entries of this warp's RoI range (four RoIs per lane and step)
   int mine = 0;
@@ -149,29 +155,49 @@ roi_bwd_plan_kernel(const void* __restrict__ rois, int dtype, int N, int n_pad, 
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-  if (lane == 0) s_wtot[warp] = mine;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int total = 0;
-    for (int i = 0; i < WARPS; ++i) total += s_wtot[i];
-    unsigned base = atomicAdd(counter, (unsigned)total);
-    if (base + (unsigned)total > capacity) {            // cannot happen with the launcher's bound; never write out of range
-      base = 0u;
-      total = 0;
+  unsigned pos_warp;
+  if (PER_WARP) {
+    unsigned base = 0u;
+    int total = mine;
+    if (lane == 0) {
+      base = atomicAdd(counter + img, (unsigned)total);
+      if (base + (unsigned)total > capacity) {          // cannot happen with the launcher's bound; never write out of range
+        base = 0u;
+        total = 0;
+      }
+      base += (unsigned)img * capacity;
+      blk_tab[(size_t)img * n_blocks + b] = make_int2((int)base, total);
     }
-    blk_tab[(size_t)img * n_blocks + b] = make_int2((int)base, total);
-    unsigned run = base;
-    for (int i = 0; i < WARPS; ++i) {
-      s_wbase[i] = run;
-      run += (unsigned)s_wtot[i];
+    total = __shfl_sync(0xffffffffu, total, 0);
+    pos_warp = __shfl_sync(0xffffffffu, base, 0);
+    if (total == 0) return;
+  } else {
+    if (lane == 0) s_wtot[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int total = 0;
+      for (int i = 0; i < WARPS; ++i) total += s_wtot[i];
+      // one bump counter per image
+      unsigned base = atomicAdd(counter + img, (unsigned)total);
+      if (base + (unsigned)total > capacity) {          // cannot happen with the launcher's bound; never write out of range
+        base = 0u;
+        total = 0;
+      }
+      base += (unsigned)img * capacity;                 // every image owns `capacity` list entries
+      blk_tab[(size_t)img * n_blocks + b] = make_int2((int)base, total);
+      unsigned run = base;
+      for (int i = 0; i < WARPS; ++i) {
+        s_wbase[i] = run;
+        run += (unsigned)s_wtot[i];
+      }
+      if (total == 0) s_wtot[0] = -1;                   // overflow / empty marker
     }
-    if (total == 0) s_wtot[0] = -1;                     // overflow / empty marker
+    __syncthreads();
+    if (s_wtot[0] < 0 || mine == 0) return;             // warp-uniform (mine is the reduced warp total)
+    pos_warp = s_wbase[warp];
   }
-  __syncthreads();
-  if (s_wtot[0] < 0 || mine == 0) return;               // warp-uniform (mine is the reduced warp total)
 
   // pass 2: the entries, RoIs in index order, (ph, pw) row-major inside a RoI
-  unsigned pos_warp = s_wbase[warp];
   unsigned* qroi = s_qroi[warp];
   unsigned short* qstart = s_qstart[warp];
   for (int round_lo = r_lo; round_lo < r_hi; round_lo += PLAN_ROUND) {
@@ -555,7 +581,7 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   const int n_pad = (N + 15) / 16 * 16;
   void *p_cnt = nullptr, *p_tab = nullptr, *p_idx = nullptr, *p_w = nullptr, *p_ym = nullptr, *p_xm = nullptr;
   int rc;
-  if ((rc = arena_get(h, stream, 256, &p_cnt))) return rc;
+  if ((rc = arena_get(h, stream, align_up((size_t)batch * sizeof(unsigned), 256), &p_cnt))) return rc;
   if ((rc = arena_get(h, stream, (size_t)batch * n_blocks * sizeof(int2), &p_tab))) return rc;
   if ((rc = arena_get(h, stream, (size_t)batch * blocks_y * n_pad, &p_ym))) return rc;
   if ((rc = arena_get(h, stream, (size_t)batch * blocks_x * n_pad, &p_xm))) return rc;
@@ -565,19 +591,27 @@ int launch_roi_bwd_blk(frcnn_handle* h, cudaStream_t stream, int mode, const flo
   uint8_t *ym = static_cast<uint8_t*>(p_ym), *xm = static_cast<uint8_t*>(p_xm);
   // plan CTAs: 8 warps sweep 2000 RoIs in one queue round each; short RoI lists take smaller CTAs (38912 of them at C1 x 64)
 #define FRCNN_PLAN(MODE, WARPS)                                                                                     \
-  roi_bwd_plan_kernel<MODE, WARPS><<<pgrid, WARPS * 32, 0, stream>>>(                                                \
-      rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, (unsigned)cap, ym, xm, static_cast<unsigned*>(p_cnt),       \
+  roi_bwd_plan_kernel<MODE, WARPS, false><<<pgrid, WARPS * 32, 0, stream>>>(                                         \
+      rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, (unsigned)(cap / batch), ym, xm, static_cast<unsigned*>(p_cnt), \
       static_cast<int2*>(p_tab), static_cast<unsigned*>(p_idx), static_cast<float4*>(p_w))
+#define FRCNN_PLAN_WARP(MODE)                                                                                       \
+  roi_bwd_plan_kernel<MODE, 8, true><<<dim3((n_blocks + 7) / 8, batch), 256, 0, stream>>>(                            \
+      rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, (unsigned)(cap / batch), ym, xm, static_cast<unsigned*>(p_cnt), \
+      static_cast<int2*>(p_tab), static_cast<unsigned*>(p_idx), static_cast<float4*>(p_w))
+#define FRCNN_PLAN_ANY(MODE)                                                                                        \
+  if (N > 1024) FRCNN_PLAN(MODE, 8); else if (N > 512) FRCNN_PLAN(MODE, 4); else FRCNN_PLAN_WARP(MODE)
   if (mode == FRCNN_ROI_RESIZE) {
     roi_bwd_mask_kernel<FRCNN_ROI_RESIZE><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm, static_cast<unsigned*>(p_cnt));
-    if (N > 1024) FRCNN_PLAN(FRCNN_ROI_RESIZE, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_RESIZE, 4); else FRCNN_PLAN(FRCNN_ROI_RESIZE, 2);
+    FRCNN_PLAN_ANY(FRCNN_ROI_RESIZE);
   } else if (compact) {
     roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm, static_cast<unsigned*>(p_cnt));
-    if (N > 1024) FRCNN_PLAN(ROI_MAX_COMPACT, 8); else if (N > 256) FRCNN_PLAN(ROI_MAX_COMPACT, 4); else FRCNN_PLAN(ROI_MAX_COMPACT, 2);
+    FRCNN_PLAN_ANY(ROI_MAX_COMPACT);
   } else {
     roi_bwd_mask_kernel<FRCNN_ROI_MAX><<<mgrid, 256, 0, stream>>>(rois, dtype, N, n_pad, H, W, P, blocks_y, blocks_x, ym, xm, static_cast<unsigned*>(p_cnt));
-    if (N > 1024) FRCNN_PLAN(FRCNN_ROI_MAX, 8); else if (N > 256) FRCNN_PLAN(FRCNN_ROI_MAX, 4); else FRCNN_PLAN(FRCNN_ROI_MAX, 2);
+    FRCNN_PLAN_ANY(FRCNN_ROI_MAX);
   }
+#undef FRCNN_PLAN_ANY
+#undef FRCNN_PLAN_WARP
 #undef FRCNN_PLAN
   FRCNN_LAUNCH_CHECK(h, "roi_bwd_mask_kernel");
   FRCNN_LAUNCH_CHECK(h, "roi_bwd_plan_kernel");
