@@ -73,10 +73,6 @@ __device__ __forceinline__ unsigned fast_div(unsigned i, FastDiv f) {
   return (t + ((i - t) >> f.s1)) >> f.s2;
 }
 
-// np.maximum / np.minimum (NaN-propagating) as single instructions
-__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-
 // x / D by the reciprocal-and-residual form of div_const (common.cuh), without its range guard
 template <int D>
 __device__ __forceinline__ float div_const_core(float x) {
@@ -349,12 +345,12 @@ proposals_kernel(const ProposalArgs p, const AnchorTable tab) {
       x = rintf(x); y = rintf(y); w = rintf(w); hgt = rintf(hgt);     // np.round: half to even
       float x2 = __fadd_rn(w, x), y2 = __fadd_rn(hgt, y);
 
-      x2 = max_nan(__fadd_rn(x, 1.0f), x2);
-      y2 = max_nan(__fadd_rn(y, 1.0f), y2);
-      x = max_nan(0.0f, x);
-      y = max_nan(0.0f, y);
-      x2 = min_nan(colmax, x2);
-      y2 = min_nan(rowmax, y2);
+      x2 = np_max(__fadd_rn(x, 1.0f), x2);
+      y2 = np_max(__fadd_rn(y, 1.0f), y2);
+      x = np_max(0.0f, x);
+      y = np_max(0.0f, y);
+      x2 = np_min(colmax, x2);
+      y2 = np_min(rowmax, y2);
 
       if (p.dense) p.dense[g] = make_float4(x, y, x2, y2);
 
