@@ -59,8 +59,16 @@ __device__ __forceinline__ float4 rpn_bbreg(int ax1, int ay1, int ax2, int ay2, 
                      (float)__dmul_rn(5.0, tw), (float)__dmul_rn(5.0, th));
 }
 
-// grid (ceil(N/256), batch).  best_gt [batch, g_max] u64 = (iou_bits << 32) | ~anchor_index,
-// zero-initialised by the caller (IoU >= 0 so float bits order like unsigned ints).
+// A warp takes ONE anchor shape and a patch of 8 x 4 feature cells, so its 32 anchors fill a small rectangle of the
+// image (anchor size + 112 x 48 pixels at stride 16) and a GT box that misses that rectangle is skipped for the whole
+// warp with four compares: every IoU of the warp would be +0 (GT area > 0 is checked, so the union is positive), which
+// changes neither the row maximum (starts at 0, strict '>') nor the column maximum (only IoU > 0 is recorded).  With one
+// thread per flat anchor index a warp held all nine shapes of 3.5 cells and its rectangle was the largest anchor's.
+// best_gt [batch, g_max] u64 = (iou_bits << 32) | ~anchor_index, zero-initialised by the caller (IoU >= 0 so float
+// bits order like unsigned ints).  Lanes are in anchor-index order (cell row-major inside the patch), which the
+// "lowest anchor index on ties" rule below relies on.
+constexpr int LBL_PATCH_W = 8, LBL_PATCH_H = 4;
+
 __global__ void __launch_bounds__(LBL_THREADS)
 label_anchors_kernel(const float* __restrict__ gt_all, const int* __restrict__ n_gt_all,
                      const int* __restrict__ img_wh, int g_max, AnchorTable tab, int rows, int cols,
@@ -79,19 +87,40 @@ label_anchors_kernel(const float* __restrict__ gt_all, const int* __restrict__ n
   }
   __syncthreads();
 
-  const int i = blockIdx.x * LBL_THREADS + tid;
-  const bool live = i < n;
-  int x1 = 0, y1 = 0, x2 = 0, y2 = 0;
-  if (live) pixel_anchor(i, tab, cols, stride, x1, y1, x2, y2);
+  const int patches_x = (cols + LBL_PATCH_W - 1) / LBL_PATCH_W, patches_y = (rows + LBL_PATCH_H - 1) / LBL_PATCH_H;
+  const int gw = blockIdx.x * (LBL_THREADS / 32) + (tid >> 5);      // (patch, anchor shape), shape fastest
+  const int a = gw % tab.n, patch = gw / tab.n;
+  if (patch >= patches_x * patches_y) return;                       // whole warp
+  const int py = patch / patches_x, px = patch - py * patches_x;
+  const int cx = px * LBL_PATCH_W + (lane & (LBL_PATCH_W - 1)), cy = py * LBL_PATCH_H + lane / LBL_PATCH_W;
+  const bool live = cx < cols && cy < rows;
+  // a lane outside the map computes on the patch's first cell (inside by construction) and stores nothing
+  const int ccx = live ? cx : px * LBL_PATCH_W, ccy = live ? cy : py * LBL_PATCH_H;
+  const int i = (ccy * cols + ccx) * tab.n + a;
+  // int(stride * (c + 0.5)) for non-negative values: exact in double (rpn_util.py:184-189)
+  const int pcx = (int)((double)stride * ((double)ccx + 0.5)), pcy = (int)((double)stride * ((double)ccy + 0.5));
+  const int x1 = pcx - (tab.w[a] >> 1), y1 = pcy - (tab.h[a] >> 1), x2 = x1 + tab.w[a], y2 = y1 + tab.h[a];
   const float fx1 = (float)x1, fy1 = (float)y1, fx2 = (float)x2, fy2 = (float)y2;
   const float a_area = __fmul_rn(__fsub_rn(fx2, fx1), __fsub_rn(fy2, fy1));
+  // the warp's rectangle (integer pixel corners; min / max over the lanes)
+  const int wx1 = __reduce_min_sync(0xffffffffu, x1), wy1 = __reduce_min_sync(0xffffffffu, y1);
+  const int wx2 = __reduce_max_sync(0xffffffffu, x2), wy2 = __reduce_max_sync(0xffffffffu, y2);
+  const float bx1 = (float)wx1, by1 = (float)wy1, bx2 = (float)wx2, by2 = (float)wy2;
 
   float best = 0.0f;      // np.amax over a row of the (N,G) matrix; G == 0 cannot happen (guarded on the host)
   int best_g = 0;
   bool first = true;
   for (int g = 0; g < G; ++g) {
     const float4 b = s_gt[g];
-    float v = live ? iou_f32(fx1, fy1, fx2, fy2, a_area, b.x, b.y, b.z, b.w, s_garea[g]) : 0.0f;
+    const float g_area = s_garea[g];
+    // no overlap with any anchor of the warp (min(x2) - max(x1) <= 0 or the same in y for every lane), finite GT
+    // corners and a positive union: all 32 IoUs are +0
+    if (g_area > 0.0f && (!(fminf(bx2, b.z) > fmaxf(bx1, b.x)) || !(fminf(by2, b.w) > fmaxf(by1, b.y))) &&
+        isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w)) {
+      first = false;      // the row maximum so far is >= 0 and '>' is strict: nothing to update
+      continue;
+    }
+    const float v = iou_f32(fx1, fy1, fx2, fy2, a_area, b.x, b.y, b.z, b.w, g_area);
     if (first || v > best) { best = v; best_g = g; first = false; }   // strict '>' keeps the first maximum
     // per-GT maximum over anchors, lowest anchor index on ties
     const unsigned bits = live ? __float_as_uint(v) : 0u;
@@ -397,7 +426,8 @@ int launch_label_anchors(frcnn_handle* h, cudaStream_t stream, const float* gt, 
   auto* best = reinterpret_cast<unsigned long long*>(ws);
   FRCNN_CUDA(h, cudaMemsetAsync(best, 0, best_bytes, stream));
   FRCNN_CUDA(h, cudaMemsetAsync(counts, 0, (size_t)batch * 2 * sizeof(int), stream));
-  dim3 grid((n + LBL_THREADS - 1) / LBL_THREADS, batch);
+  const int patches = ((cols + LBL_PATCH_W - 1) / LBL_PATCH_W) * ((rows + LBL_PATCH_H - 1) / LBL_PATCH_H);
+  dim3 grid((patches * tab.n + LBL_THREADS / 32 - 1) / (LBL_THREADS / 32), batch);
   label_anchors_kernel<<<grid, LBL_THREADS, 0, stream>>>(gt, n_gt, img_wh, g_max, tab, rows, cols, stride, n,
                                                         can_use, is_pos, reinterpret_cast<float4*>(bbreg), best);
   FRCNN_LAUNCH_CHECK(h, "label_anchors_kernel");
