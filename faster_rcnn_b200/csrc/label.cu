@@ -267,30 +267,26 @@ apply_sampling_kernel(unsigned char* __restrict__ can_use_all, const unsigned ch
   }
 }
 
-// one thread per location (y, x) of one image: writes 2A bytes + 8A floats contiguous per cell.
+// one thread per anchor: two 16-byte stores into the cell's y_bbreg row (the selector repeated four times, the four
+// targets) and two bytes into its y_class row.  The first version ran one thread per float of y_bbreg with a 64-bit
+// division and modulo by 8A each: 0.125 ms per 128 images for 143 MB, six times the HBM time.
 __global__ void __launch_bounds__(LBL_THREADS)
 pack_rpn_kernel(const unsigned char* __restrict__ can_use, const unsigned char* __restrict__ is_pos,
-                const float* __restrict__ bbreg, int n_loc, int A, unsigned char* __restrict__ y_class,
-                float* __restrict__ y_bbreg) {
-  // flat over (image, location, 8A slots of y_bbreg); y_class handled by the first 2A slots
-  const size_t total = (size_t)gridDim.y * 0 + (size_t)n_loc * 8 * A;
+                const float4* __restrict__ bbreg, int n_loc, int A, unsigned char* __restrict__ y_class,
+                float4* __restrict__ y_bbreg) {
   const int img = blockIdx.y;
-  for (size_t e = (size_t)blockIdx.x * LBL_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * LBL_THREADS) {
-    const int loc = (int)(e / (8 * A)), s = (int)(e % (8 * A));
-    const size_t abase = ((size_t)img * n_loc + loc) * A;
-    float v;
-    if (s < 4 * A) {
-      const int a = s >> 2;                                   // np.repeat(sel, 4, axis=2)
-      v = (can_use[abase + a] && is_pos[abase + a]) ? 1.0f : 0.0f;
-    } else {
-      v = bbreg[abase * 4 + (s - 4 * A)];
-    }
-    y_bbreg[((size_t)img * n_loc + loc) * 8 * A + s] = v;
-    if (s < 2 * A) {
-      const unsigned char c = (s < A) ? can_use[abase + s] : is_pos[abase + s - A];
-      y_class[((size_t)img * n_loc + loc) * 2 * A + s] = c;
-    }
-  }
+  const unsigned t = blockIdx.x * LBL_THREADS + threadIdx.x;      // anchor inside the image
+  if (t >= (unsigned)n_loc * (unsigned)A) return;
+  const unsigned loc = t / (unsigned)A, a = t - loc * (unsigned)A;
+  const size_t anchor = (size_t)img * n_loc * A + t, cell = (size_t)img * n_loc + loc;
+  const unsigned char cu = can_use[anchor], ip = is_pos[anchor];
+  const float sel = (cu && ip) ? 1.0f : 0.0f;                     // np.repeat(sel, 4, axis=2)
+  float4* row = y_bbreg + cell * 2 * A;                           // 8A floats per cell
+  row[a] = make_float4(sel, sel, sel, sel);
+  row[A + a] = bbreg[anchor];
+  unsigned char* crow = y_class + cell * 2 * A;
+  crow[a] = cu;
+  crow[A + a] = ip;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -457,10 +453,11 @@ int launch_pack_rpn(frcnn_handle* h, cudaStream_t stream, uint8_t* can_use, cons
                                                                off_neg_offsets, words);
     FRCNN_LAUNCH_CHECK(h, "apply_sampling_kernel");
   }
-  const size_t per_img = (size_t)n_loc * 8 * A;
-  int gx = (int)((per_img + LBL_THREADS - 1) / LBL_THREADS);
-  if (gx > 4096) gx = 4096;
-  pack_rpn_kernel<<<dim3(gx, batch), LBL_THREADS, 0, stream>>>(can_use, is_pos, bbreg, n_loc, A, y_class, y_bbreg);
+  if ((reinterpret_cast<uintptr_t>(bbreg) | reinterpret_cast<uintptr_t>(y_bbreg)) & 15u)
+    return fail(h, FRCNN_ERR_INVALID, "pack_rpn_targets: bbreg and y_bbreg must be 16-byte aligned%s%s");
+  const unsigned per_img = (unsigned)n_loc * (unsigned)A;
+  pack_rpn_kernel<<<dim3((per_img + LBL_THREADS - 1) / LBL_THREADS, batch), LBL_THREADS, 0, stream>>>(
+      can_use, is_pos, reinterpret_cast<const float4*>(bbreg), n_loc, A, y_class, reinterpret_cast<float4*>(y_bbreg));
   FRCNN_LAUNCH_CHECK(h, "pack_rpn_kernel");
   return FRCNN_OK;
 }
