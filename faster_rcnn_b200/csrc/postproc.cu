@@ -11,7 +11,7 @@
 
 namespace frcnn {
 
-constexpr int PP_THREADS = 256;
+constexpr int PP_THREADS = 1024;     // one CTA per image: 32 warps so that every class has a warp in the NMS phase
 constexpr int PP_MAX_ROWS = 1024;
 constexpr int PP_MAX_CLASSES = 128;
 
@@ -24,12 +24,13 @@ det_postprocess_kernel(const BoxI16* __restrict__ rois_all, const float* __restr
                        int bg, int stride, float det_thr, double nms_thr, int max_boxes,
                        int* __restrict__ det_boxes, float* __restrict__ det_probs, int* __restrict__ det_cls,
                        int* __restrict__ det_count) {
-  // dynamic smem, sized by M: double4 box[M] | double area[M] | float prob[M] | short cls[M] |
+  // dynamic smem, sized by M: double4 box[M] | double area[M] | u64 key[M] | float prob[M] | short cls[M] |
   // short sorted[M] | short keep[M] | uchar dead[M]
   extern __shared__ __align__(32) unsigned char pp_smem[];
   double4* s_box = reinterpret_cast<double4*>(pp_smem);      // decoded boxes (by row)
   double* s_area = reinterpret_cast<double*>(s_box + M);     // areas in per-class visit order
-  float* s_prob = reinterpret_cast<float*>(s_area + M);
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_area + M);   // class << 48 | mono(prob) << 16 | row
+  float* s_prob = reinterpret_cast<float*>(s_key + M);
   short* s_cls = reinterpret_cast<short*>(s_prob + M);       // class of the row, -1 = dropped
   short* s_sorted = s_cls + M;                               // row ids in (class order, visit order)
   short* s_keep = s_sorted + M;                              // per-class pick lists (positions in the class)
@@ -50,12 +51,12 @@ det_postprocess_kernel(const BoxI16* __restrict__ rois_all, const float* __restr
 
   // 1+2: class choice and float64 decode
   for (int r = tid; r < M; r += PP_THREADS) {
-    if (r >= m_live) { s_cls[r] = -1; continue; }
+    if (r >= m_live) { s_cls[r] = -1; s_key[r] = ~0ull; continue; }
     const float* p = ocls + (size_t)r * K;
     int c = 0;
     float conf = p[0];
     for (int q = 1; q < K; ++q) { const float v = p[q]; if (v > conf) { conf = v; c = q; } }
-    if (c == bg || conf < det_thr) { s_cls[r] = -1; continue; }
+    if (c == bg || conf < det_thr) { s_cls[r] = -1; s_key[r] = ~0ull; continue; }
     const float* t = oreg + (size_t)r * 4 * (K - 1) + 4 * c;
     const float tx = __fdiv_rn(t[0], 10.f), ty = __fdiv_rn(t[1], 10.f), tw = __fdiv_rn(t[2], 5.f), th = __fdiv_rn(t[3], 5.f);
     const BoxI16 b = rois[r];
@@ -70,39 +71,61 @@ det_postprocess_kernel(const BoxI16* __restrict__ rois_all, const float* __restr
     s_box[r] = o;
     s_prob[r] = conf;
     s_cls[r] = (short)c;
+    s_key[r] = ((unsigned long long)c << 48) | ((unsigned long long)mono_key(conf) << 16) | (unsigned)r;
     atomicMin(&s_first[c], r);
     atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
 
-  // 3: classes in order of first appearance, segment offsets
-  if (tid == 0) {
+  // 3: classes in order of first appearance, segment offsets (warp 0: a class's place = the number of present classes
+  // that appear earlier; offsets by a running warp scan over the places)
+  if (warp == 0) {
     int nc = 0;
-    for (int c = 0; c < K; ++c) if (s_cnt[c] > 0) s_order[nc++] = c;
-    for (int i = 1; i < nc; ++i) {          // insertion sort by first row (nc <= K, tiny)
-      const int c = s_order[i];
-      int j = i - 1;
-      while (j >= 0 && s_first[s_order[j]] > s_first[c]) { s_order[j + 1] = s_order[j]; --j; }
-      s_order[j + 1] = c;
+    for (int c0 = 0; c0 < K; c0 += 32) nc += __popc(__ballot_sync(0xffffffffu, c0 + lane < K && s_cnt[c0 + lane] > 0));
+    for (int c = lane; c < K; c += 32) {
+      if (s_cnt[c] == 0) continue;
+      const int f = s_first[c];
+      int place = 0;
+      for (int q = 0; q < K; ++q) place += (s_cnt[q] > 0 && s_first[q] < f) ? 1 : 0;     // first rows are distinct
+      s_order[place] = c;
     }
-    int off = 0;
-    for (int i = 0; i < nc; ++i) { s_off[s_order[i]] = off; off += s_cnt[s_order[i]]; }
-    s_ncls = nc;
+    __syncwarp();
+    int run = 0;
+    for (int i0 = 0; i0 < nc; i0 += 32) {
+      const int i = i0 + lane;
+      const int cnt = i < nc ? s_cnt[s_order[i]] : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (i < nc) s_off[s_order[i]] = run + incl - cnt;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_ncls = nc;
   }
   __syncthreads();
 
-  // 4a: visit rank inside the class: (prob desc, position-in-class desc)
-  for (int r = tid; r < M; r += PP_THREADS) {
-    const int c = s_cls[r];
-    if (c < 0) continue;
-    const unsigned kr = mono_key(s_prob[r]);
-    int rank = 0;
-    for (int q = 0; q < M; ++q) {
-      if (s_cls[q] != c || q == r) continue;
-      const unsigned kq = mono_key(s_prob[q]);
-      rank += (kq > kr) || (kq == kr && q > r);
+  // 4a: visit rank inside the class: (prob desc, position-in-class desc) = the number of rows of the class with a larger
+  // packed key.  Rows are spread over the lanes of a warp (eight partial counts per row, reduced by shuffles): the
+  // first version walked all M rows per thread with two dependent shared loads and a branch per step (74 k cycles).
+  {
+    constexpr int PARTS = 8;                           // lanes per row
+    const int part = lane & (PARTS - 1);
+    for (int base = warp * (32 / PARTS); base < M; base += PP_THREADS / PARTS) {    // warp-uniform: shuffles inside
+      const int r = base + lane / PARTS;
+      const unsigned long long kr = r < M ? s_key[r] : ~0ull;
+      const bool row_live = kr != ~0ull;
+      int rank = 0;
+      for (int q = part; q < M; q += PARTS) {
+        const unsigned long long kq = s_key[q];
+        rank += (((kq ^ kr) >> 48) == 0ull && kq > kr) ? 1 : 0;        // dropped rows (~0) never share a live row's class
+      }
+#pragma unroll
+      for (int d = 1; d < PARTS; d <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
+      if (row_live && part == 0) s_sorted[s_off[(int)(kr >> 48)] + rank] = (short)r;
     }
-    s_sorted[s_off[c] + rank] = (short)r;
   }
   __syncthreads();
   const int total_rows = (s_ncls > 0) ? s_off[s_order[s_ncls - 1]] + s_cnt[s_order[s_ncls - 1]] : 0;
@@ -147,20 +170,20 @@ det_postprocess_kernel(const BoxI16* __restrict__ rois_all, const float* __restr
     det_count[img] = off;
   }
   __syncthreads();
-  for (int ci = 0; ci < s_ncls; ++ci) {
+  for (int o_row = tid; o_row < s_koff[s_ncls]; o_row += PP_THREADS) {
+    int ci = 0;
+    while (s_koff[ci + 1] <= o_row) ++ci;                 // class segment of this output row (at most K steps)
     const int c = s_order[ci];
-    const int off = s_off[c];
-    for (int q = tid; q < s_nkeep[c]; q += PP_THREADS) {
-      const int row = s_sorted[off + s_keep[off + q]];
-      const double4 b = s_box[row];
-      const size_t o = (size_t)img * M + s_koff[ci] + q;
-      det_boxes[4 * o + 0] = (int)rint(__ddiv_rn(b.x, ratio));
-      det_boxes[4 * o + 1] = (int)rint(__ddiv_rn(b.y, ratio));
-      det_boxes[4 * o + 2] = (int)rint(__ddiv_rn(b.z, ratio));
-      det_boxes[4 * o + 3] = (int)rint(__ddiv_rn(b.w, ratio));
-      det_probs[o] = s_prob[row];
-      det_cls[o] = c;
-    }
+    const int off = s_off[c], q = o_row - s_koff[ci];
+    const int row = s_sorted[off + s_keep[off + q]];
+    const double4 b = s_box[row];
+    const size_t o = (size_t)img * M + o_row;
+    det_boxes[4 * o + 0] = (int)rint(__ddiv_rn(b.x, ratio));
+    det_boxes[4 * o + 1] = (int)rint(__ddiv_rn(b.y, ratio));
+    det_boxes[4 * o + 2] = (int)rint(__ddiv_rn(b.z, ratio));
+    det_boxes[4 * o + 3] = (int)rint(__ddiv_rn(b.w, ratio));
+    det_probs[o] = s_prob[row];
+    det_cls[o] = c;
   }
   for (int q = s_koff[s_ncls] + tid; q < M; q += PP_THREADS) {
     const size_t o = (size_t)img * M + q;
@@ -176,7 +199,7 @@ int launch_det_postprocess(frcnn_handle* h, cudaStream_t stream, const int16_t* 
                            float* det_probs, int32_t* det_cls, int32_t* det_count) {
   if (M > PP_MAX_ROWS || K > PP_MAX_CLASSES)
     return fail(h, FRCNN_ERR_UNSUPPORTED, "det_postprocess: more than 1024 rows or 128 classes per image%s%s");
-  const size_t smem = (size_t)M * (32 + 8 + 4 + 2 + 2 + 2 + 1) + 64;
+  const size_t smem = (size_t)M * (32 + 8 + 8 + 4 + 2 + 2 + 2 + 1) + 64;
   FRCNN_CUDA(h, cudaFuncSetAttribute(det_postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   det_postprocess_kernel<<<batch, PP_THREADS, smem, stream>>>(reinterpret_cast<const BoxI16*>(rois), out_cls, out_reg,
                                                            ratio, n_rows, M, K, bg, stride, (float)det_thr, nms_thr,
