@@ -18,7 +18,7 @@
 
 namespace frcnn {
 
-constexpr int LOSS_THREADS = 512;
+constexpr int LOSS_THREADS = 1024;    // one CTA per image: its warps have to hide the log / exp chains themselves
 
 // deterministic block sum of `K` doubles per thread; result valid in every thread
 template <int K>
