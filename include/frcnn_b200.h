@@ -162,7 +162,8 @@ FRCNN_API int frcnn_label_anchors(frcnn_handle* h, void* stream, const float* gt
  *   come from frcnn_label_anchors); off_*_offsets [batch+1] i32 delimit each image's
  *   slice.  The anchors at those ranks get can_use = 0 (in place, like the reference),
  *   then y_class [batch,R,C,2A] u8 = [can_use | is_pos] and y_bbreg [batch,R,C,8A] f32 =
- *   [repeat(is_pos & can_use, 4) | targets] are written. */
+ *   [repeat(is_pos & can_use, 4) | targets] are written.  bbreg and y_bbreg must be
+ *   16-byte aligned (FRCNN_ERR_INVALID otherwise). */
 FRCNN_API int frcnn_pack_rpn_targets(frcnn_handle* h, void* stream, uint8_t* can_use, const uint8_t* is_pos,
                                      const float* bbreg, const int32_t* off_pos,
                                      const int32_t* off_pos_offsets, const int32_t* off_neg,
