@@ -82,9 +82,12 @@ resize_cubic_kernel(const unsigned char* __restrict__ src, int src_h, int src_w,
 // integer divisions per horizontal sum, three float64-pipe operations per value); this one about 30.
 // Used while eight output rows span at most TILE_ROWS source rows (any enlargement, reductions down to about 1/4) and
 // the image has 1, 3 or 4 channels; the per-pixel kernel takes the rest.
-constexpr int TILE_W = 32, TILE_H = 8, TILE_ROWS = 40;
+// Two tile heights: 32 output rows per CTA (four per thread: the column's taps, the mean table and the tile set-up
+// are paid once for four pixels, and neighbouring output rows share more source rows) while they span at most 72 source
+// rows (scale <= 2.1), else 8 rows / 40 source rows.
+constexpr int TILE_W = 32;
 
-template <int CN>
+template <int CN, int TILE_H, int TILE_ROWS>
 __global__ void __launch_bounds__(256)
 resize_cubic_tile_kernel(const unsigned char* __restrict__ src, int src_h, int src_w, int dst_h, int dst_w,
                          const CubicTap* __restrict__ xt, const CubicTap* __restrict__ yt, const float* __restrict__ lut,
@@ -102,7 +105,7 @@ resize_cubic_tile_kernel(const unsigned char* __restrict__ src, int src_h, int s
 #pragma unroll
   for (int k = 0; k < 4; ++k) xo[k] = min(max(tx.s + k, 0), src_w - 1) * CN;
   const unsigned char* s_img = src + (size_t)img * src_h * src_w * CN;
-  for (int row = wy; row < n_rows; row += TILE_H) {
+  for (int row = wy; row < n_rows; row += 8) {
     const unsigned char* rp = s_img + (size_t)min(max(r0 + row, 0), src_h - 1) * src_w * CN;
 #pragma unroll
     for (int c = 0; c < CN; ++c)
@@ -110,19 +113,21 @@ resize_cubic_tile_kernel(const unsigned char* __restrict__ src, int src_h, int s
                             (int)rp[xo[3] + c] * tx.c[3];
   }
   __syncthreads();
-  const int dy = dy0 + wy;
-  if (dx0 + x >= dst_w || dy >= dst_h) return;
-  const CubicTap ty = yt[dy];
-  const int rr = ty.s - r0;
+  if (dx0 + x >= dst_w) return;
   const int ox = flip ? dst_w - 1 - dx : dx;
-  const size_t o = (((size_t)img * dst_h + dy) * dst_w + ox) * CN;
+#pragma unroll 1
+  for (int dy = dy0 + wy; dy < min(dy0 + TILE_H, dst_h); dy += 8) {
+    const CubicTap ty = yt[dy];
+    const int rr = ty.s - r0;
+    const size_t o = (((size_t)img * dst_h + dy) * dst_w + ox) * CN;
 #pragma unroll
-  for (int c = 0; c < CN; ++c) {
-    const int acc = hs[rr][c * TILE_W + x] * ty.c[0] + hs[rr + 1][c * TILE_W + x] * ty.c[1] + hs[rr + 2][c * TILE_W + x] * ty.c[2] +
-                    hs[rr + 3][c * TILE_W + x] * ty.c[3];
-    const int v = min(255, max(0, (acc + (1 << 21)) >> 22));
-    if (out_u8) out_u8[o + c] = (unsigned char)v;
-    if (out_f32) out_f32[o + c] = s_lut[c][v];
+    for (int c = 0; c < CN; ++c) {
+      const int acc = hs[rr][c * TILE_W + x] * ty.c[0] + hs[rr + 1][c * TILE_W + x] * ty.c[1] + hs[rr + 2][c * TILE_W + x] * ty.c[2] +
+                      hs[rr + 3][c * TILE_W + x] * ty.c[3];
+      const int v = min(255, max(0, (acc + (1 << 21)) >> 22));
+      if (out_u8) out_u8[o + c] = (unsigned char)v;
+      if (out_f32) out_f32[o + c] = s_lut[c][v];
+    }
   }
 }
 
@@ -169,21 +174,22 @@ int launch_image_resize(frcnn_handle* h, cudaStream_t stream, const uint8_t* src
   if (mean_host)
     for (int c = 0; c < cn && c < 4; ++c) m[c] = mean_host[c];
   dim3 grid((dst_w + 31) / 32, (dst_h + 7) / 8, batch);
-  // source rows touched by eight consecutive output rows: at most ceil(7 * src_h / dst_h) + 5 (first taps of rows that
-  // are 7 apart differ by at most ceil(7 * scale) + 1, plus the four taps)
-  const long long span = (7LL * src_h + dst_h - 1) / dst_h + 5;
-  if ((cn == 1 || cn == 3 || cn == 4) && span <= TILE_ROWS) {
+  // source rows touched by T consecutive output rows: at most ceil((T - 1) * src_h / dst_h) + 5 (first taps of rows
+  // that are T - 1 apart differ by at most ceil((T - 1) * scale) + 1, plus the four taps)
+  const long long span8 = (7LL * src_h + dst_h - 1) / dst_h + 5, span32 = (31LL * src_h + dst_h - 1) / dst_h + 5;
+  if ((cn == 1 || cn == 3 || cn == 4) && span8 <= 40) {
     void* lut = nullptr;
     if ((rc = arena_get(h, stream, 4 * 256 * sizeof(float), &lut))) return rc;
     float* lutf = static_cast<float*>(lut);
     mean_lut_kernel<<<1, 256, 0, stream>>>(lutf, m[0], m[1], m[2], m[3]);
     FRCNN_LAUNCH_CHECK(h, "mean_lut_kernel");
-    if (cn == 1)
-      resize_cubic_tile_kernel<1><<<grid, 256, 0, stream>>>(src, src_h, src_w, dst_h, dst_w, xt, yt, lutf, flip, out_u8, out_f32);
-    else if (cn == 3)
-      resize_cubic_tile_kernel<3><<<grid, 256, 0, stream>>>(src, src_h, src_w, dst_h, dst_w, xt, yt, lutf, flip, out_u8, out_f32);
-    else
-      resize_cubic_tile_kernel<4><<<grid, 256, 0, stream>>>(src, src_h, src_w, dst_h, dst_w, xt, yt, lutf, flip, out_u8, out_f32);
+    const bool tall = span32 <= 72;
+    const dim3 tgrid((dst_w + 31) / 32, tall ? (dst_h + 31) / 32 : (dst_h + 7) / 8, batch);
+#define FRCNN_TILE(CN)                                                                                                  \
+  if (tall) resize_cubic_tile_kernel<CN, 32, 72><<<tgrid, 256, 0, stream>>>(src, src_h, src_w, dst_h, dst_w, xt, yt, lutf, flip, out_u8, out_f32); \
+  else resize_cubic_tile_kernel<CN, 8, 40><<<tgrid, 256, 0, stream>>>(src, src_h, src_w, dst_h, dst_w, xt, yt, lutf, flip, out_u8, out_f32)
+    if (cn == 1) { FRCNN_TILE(1); } else if (cn == 3) { FRCNN_TILE(3); } else { FRCNN_TILE(4); }
+#undef FRCNN_TILE
     FRCNN_LAUNCH_CHECK(h, "resize_cubic_tile_kernel");
     return FRCNN_OK;
   }
