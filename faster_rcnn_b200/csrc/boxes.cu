@@ -19,7 +19,15 @@ cross_ious_kernel(const void* __restrict__ boxes, int n, const float* __restrict
                   float* __restrict__ iou) {
   const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (e >= (size_t)n * g_count) return;
-  const int i = (int)(e / g_count), g = (int)(e % g_count);
+  // 32-bit division whenever the matrix has fewer than 2^32 elements (a 64-bit division is ~100 instructions)
+  int i, g;
+  if (((unsigned long long)n * (unsigned)g_count >> 32) == 0ull) {
+    i = (int)((unsigned)e / (unsigned)g_count);
+    g = (int)((unsigned)e - (unsigned)i * (unsigned)g_count);
+  } else {
+    i = (int)(e / g_count);
+    g = (int)(e % g_count);
+  }
   float x1, y1, x2, y2, a_area;
   if (I16) {
     const short* p = reinterpret_cast<const short*>(boxes) + 4 * (size_t)i;
