@@ -521,7 +521,10 @@ int launch_nms_i16(frcnn_handle* h, cudaStream_t stream, const int16_t* boxes, c
     // measured: 16 (non-portable cluster size) at batch 1: 0.81 -> 0.74 ms at 12000 -> 2000; 2 at batch 64
     while (cl < 16 && (long long)batch * cl * 2 <= h->sm_count) cl <<= 1;
   } else if (max_keep >= 256) {
-    while (cl < 2 && (long long)batch * cl * 2 <= h->sm_count) cl <<= 1;
+    // inference setting (8000 -> 300): the per-tile fixed phases dominate, a cluster buys little -- 58.2 / 59.1 / 55.3 /
+    // 54.2 / 55.1 us with 1 / 2 / 4 / 8 / 16 CTAs on clustered scores, 25-27 us on uniform ones -- so take up to 8
+    // while SMs are idle
+    while (cl < 8 && (long long)batch * cl * 2 <= h->sm_count) cl <<= 1;
   }
   if (getenv("FRCNN_NMS_CL")) cl = atoi(getenv("FRCNN_NMS_CL"));     // experiment knob
   if (cl < 1 || cl > 16 || (cl & (cl - 1))) cl = 1;
